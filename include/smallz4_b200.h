@@ -1,0 +1,95 @@
+/*
+ * smallz4_b200.h -- C ABI of libsmallz4_b200.so, the B200-native replacement for the hot path of
+ * smalLZ4 (optimal-parse LZ4 compression).  Plain pointers and sizes only; bind it from C, C++
+ * (include/smallz4.h is the drop-in class), cgo, JNI or ctypes.
+ *
+ * What each entry point replaces in the reference (/root/reference):
+ *   sz4_lz4()                smallz4::lz4(getBytes, sendBytes, maxChainLength, dictionary,
+ *                            useLegacyFormat, userPtr)                       smallz4.h:47-64
+ *                            -> smallz4::compress()                          smallz4.h:476-814
+ *   sz4_compress_host()      the same call with in-memory callbacks (what smallz4.cpp:66-117
+ *                            getBytesFromIn / sendBytesToOut do with FILE*)
+ *   sz4_compress_device()    the per-block loop of compress() (smallz4.h:547-806) for input that
+ *                            is already resident in HBM; used for multi-GPU shards
+ *   sz4_version()            smallz4::getVersion()                           smallz4.h:67
+ *   SZ4_LEVEL_*              ShortChainsGreedy / ShortChainsLazy             smallz4.h:74-80
+ *
+ * Output is byte-identical to the reference's for the same input, maxChainLength, dictionary and
+ * format.  All compute runs in hand-written sm_100a CUDA kernels; there is no CPU fallback:
+ * every call fails with SZ4_ERR_CUDA when no CUDA device is usable.
+ */
+#ifndef SMALLZ4_B200_H
+#define SMALLZ4_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SZ4_OK             0
+#define SZ4_ERR_CUDA      -1   /* no device / CUDA runtime error (sz4_last_error has the text) */
+#define SZ4_ERR_ARG       -2   /* invalid argument                                             */
+#define SZ4_ERR_NOMEM     -3   /* host or device allocation failed                             */
+#define SZ4_ERR_DST_SMALL -4   /* destination buffer too small                                 */
+
+#define SZ4_LEVEL_GREEDY_MAX 3      /* smallz4::ShortChainsGreedy */
+#define SZ4_LEVEL_LAZY_MAX   6      /* smallz4::ShortChainsLazy   */
+#define SZ4_MAX_CHAIN_DEFAULT 65535 /* smallz4::MaxChainLength: level -9 */
+
+/* same signatures as smallz4::GET_BYTES / smallz4::SEND_BYTES (smallz4.h:42-44) */
+typedef size_t (*sz4_get_bytes)(void* data, size_t numBytes, void* userPtr);
+typedef void   (*sz4_send_bytes)(const void* data, size_t numBytes, void* userPtr);
+
+typedef struct sz4_ctx sz4_ctx;
+
+/* device < 0: current device.  The context owns its stream and device buffers; one per thread. */
+int         sz4_create(sz4_ctx** out, int device);
+void        sz4_destroy(sz4_ctx* ctx);
+const char* sz4_last_error(const sz4_ctx* ctx);
+const char* sz4_version(void);
+
+/* tuning / test knobs: "batch_blocks" (blocks per device batch), "block_size" (tests only: a multiple
+   of 65536, >= 131072; 0 = format default), "stage_bulk" (1 = cp.async.bulk staging, 0 = plain loads),
+   "debug_keep" (keep intermediates of the last batch for sz4_debug_fetch) */
+int sz4_set_option(sz4_ctx* ctx, const char* name, long long value);
+
+/* worst-case size of the frame produced for n input bytes */
+size_t sz4_compress_bound(size_t n, int use_legacy_format);
+
+/* drop-in for smallz4::lz4(): pulls the whole stream through get_bytes, pushes the frame through
+   send_bytes.  max_chain_length 0..65535 (levels -0..-8 map to 0..8, -9 to 65535, smallz4.cpp:175,233) */
+int sz4_lz4(sz4_ctx* ctx, sz4_get_bytes get_bytes, sz4_send_bytes send_bytes,
+            unsigned short max_chain_length, const unsigned char* dictionary, size_t dictionary_len,
+            int use_legacy_format, void* user_ptr);
+
+/* host buffer -> host buffer (pinned buffers make the copies asynchronous) */
+int sz4_compress_host(sz4_ctx* ctx, const void* src, size_t n, void* dst, size_t dst_capacity, size_t* frame_len,
+                      unsigned short max_chain_length, const unsigned char* dictionary, size_t dictionary_len,
+                      int use_legacy_format);
+
+/* Device-resident whole blocks.  d_src points at `halo` bytes of history followed by `n` bytes that
+   start on a block border of the stream; is_stream_first / is_stream_last say whether the range
+   contains the first / last block of the stream.  Writes the concatenated [size][payload] block
+   records (no frame header, no end mark) to d_dst (device) and their total length to *segment_len.
+   This is the unit one GPU of a sharded job produces; blocks depend only on their 64 KiB halo. */
+int sz4_compress_device(sz4_ctx* ctx, const void* d_src, size_t halo, size_t n, int is_stream_first, int is_stream_last,
+                        void* d_dst, size_t dst_capacity, size_t* segment_len,
+                        unsigned short max_chain_length, int use_legacy_format, void* cuda_stream);
+
+/* frame header / end mark (smallz4.h:479-496, 809-813) for callers that assemble shards themselves */
+size_t sz4_frame_header(unsigned char* dst, int use_legacy_format);
+size_t sz4_frame_end(unsigned char* dst, int use_legacy_format);
+
+/* milliseconds the device spent in the kernels of the last call and number of kernel launches */
+int sz4_last_stats(const sz4_ctx* ctx, double* kernel_ms, unsigned long long* launches);
+
+/* test hook: copy an intermediate array of the last batch to the host (needs option debug_keep=1).
+   what: "pe" u16, "len_found" u32, "dist_found" u16, "len_final" u32, "cost" u32; count = elements */
+int sz4_debug_fetch(sz4_ctx* ctx, const char* what, void* dst, size_t count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,253 @@
+// sz4_parse.cuh -- phase 3a: backward cost DP (smallz4.h:376 estimateCosts) and the walk along the
+// chosen parse (the control flow of smallz4.h:259 selectBestMatches), one warp per LZ4 block.
+//
+// estimateCosts, for i from n-6 down to 0:
+//     literal:  cost[i+1] + 1 (+1 when the run of literal decisions behind i reaches 15, 270, 525, ...)
+//     match L in 4..len[i]:  cost[i+L] + 3 + e(L),  e(L) = 0 (L<=18) else 1 + (L-19)/255
+//     smallest cost wins; among equal costs the longest match, and a match beats the literal.
+//     len >= 65299 at distance 1 is taken unpriced (smallz4.h:410-416).
+// The recurrence is sequential in i, but a candidate L >= 4 only needs costs that are at least four
+// positions old.  The warp therefore works on groups of 32 positions:
+//   far phase   (lane = position): candidates that end two or more groups ahead.  They are
+//               grouped by e(L) into classes of 255 consecutive lengths; the minimum of a class is a
+//               range-minimum query answered from three sparse-table levels (windows of 32/64/128
+//               costs, ties resolved towards the larger index) that the warp maintains as it goes.
+//               A match of length 60 000 costs ~470 table reads instead of 60 000 additions.
+//   near phase  (32 sequential steps): candidates inside this group and the next one live in two
+//               registers per lane; one __reduce_min_sync per position picks the best of them.
+#pragma once
+#include "sz4_device.cuh"
+
+namespace sz4
+{
+struct DpScratch
+{
+  uint32_t* cost;   // cost[i]                                   (indexed by batch position)
+  uint32_t* st5;    // (min cost over [i, i+31])  << 8 | (255 - offset of the LAST minimum)
+  uint32_t* st6;    // same over [i, i+63]
+  uint32_t* st7;    // same over [i, i+127]
+};
+
+__device__ __forceinline__ uint32_t match_extra(uint32_t len) { return len < 19 ? 0 : 1 + (len - 19) / 255; }
+
+// candidate = (cost << 32) | length ; better = smaller cost, then larger length
+__device__ __forceinline__ void take_better(uint32_t& best_cost, uint32_t& best_len, uint32_t c, uint32_t l)
+{
+  if (c < best_cost || (c == best_cost && l > best_len)) { best_cost = c; best_len = l; }
+}
+
+// minimum of cost[a..b] (a <= b, b-a < 255), ties -> largest index.  All positions two groups or more ahead.
+__device__ __forceinline__ void range_min(const DpScratch& s, uint32_t a, uint32_t b, uint32_t& out_cost, uint32_t& out_idx)
+{
+  const uint32_t span = b - a + 1;
+  if (span < 32)
+  {
+    uint32_t bc = 0xffffffffu, bi = a;
+    for (uint32_t j = a; j <= b; j++)
+    {
+      uint32_t c = __ldcg(s.cost + j);
+      if (c <= bc) { bc = c; bi = j; }
+    }
+    out_cost = bc; out_idx = bi;
+    return;
+  }
+  const uint32_t* tab = span >= 128 ? s.st7 : (span >= 64 ? s.st6 : s.st5);
+  const uint32_t w = span >= 128 ? 128 : (span >= 64 ? 64 : 32);
+  const uint32_t a2 = b + 1 - w;
+  const uint32_t v1 = __ldcg(tab + a), v2 = __ldcg(tab + a2);
+  const uint32_t c1 = v1 >> 8, i1 = a + (255 - (v1 & 255));
+  const uint32_t c2 = v2 >> 8, i2 = a2 + (255 - (v2 & 255));
+  if (c2 < c1 || (c2 == c1 && i2 > i1)) { out_cost = c2; out_idx = i2; }
+  else { out_cost = c1; out_idx = i1; }
+}
+
+__global__ void __launch_bounds__(32)
+k_dp(uint32_t* mlen, const uint16_t* mdist, DpScratch s, Geom g)
+{
+  const uint32_t j = blockIdx.x;
+  if (j >= g.n_blocks) return;
+  const uint32_t b = block_begin(g, j), n = block_len(g, j);
+  if (n <= kEndNoMatch) return;                                  // smallz4.h:755
+  const uint32_t lane = threadIdx.x;
+  const uint32_t last_priced = n - (1 + kEndLiterals);           // i runs from n-6 down to 0
+  const uint32_t top_group = (n - 1) / 32;
+
+  uint32_t run = kEndLiterals;                                   // numLiterals, uniform
+  uint32_t next_cost = 0;                                        // cost[i+1], uniform
+  uint32_t prv = 0;                                              // cost of (group+1)*32 + lane
+  uint32_t p5 = 0xffffffffu, p6a = 0xffffffffu, p6b = 0xffffffffu;   // st5 of group+1, st6 of group+1 / group+2
+
+  for (int32_t grp = (int32_t)top_group; grp >= 0; grp--)
+  {
+    const uint32_t i0 = (uint32_t)grp * 32;
+    const uint32_t i = i0 + lane;                                // this lane's position (block relative)
+    const bool priced = i <= last_priced;
+    uint32_t M = 0, D = 0;
+    if (i < n) { M = mlen[b + i]; D = mdist[b + i]; }
+    if (!priced) M = 0;
+
+    // ------------------------------ far phase: candidates ending at >= i0 + 64
+    uint32_t far_cost = 0xffffffffu, far_len = 0;
+    bool forced = false;
+    if (M >= kSameLetter && D == 1)
+    {
+      forced = true;                                             // smallz4.h:410-416
+      far_cost = __ldcg(s.cost + b + i + M) + 1 + 2 + 1 + (M - 19) / 255;
+      far_len = M;
+    }
+    else if (M >= kMinMatch && i + M >= i0 + 64)
+    {
+      uint32_t lo = i0 + 64 - i;                                 // first far length (33..64)
+      while (lo <= M)
+      {
+        // class of lo: [4,18] e=0 ; [19+255(c-1), 18+255c] e=c
+        uint32_t e = match_extra(lo);
+        uint32_t hi = e == 0 ? 18 : 18 + 255 * e;
+        if (hi > M) hi = M;
+        uint32_t c, at;
+        range_min(s, b + i + lo, b + i + hi, c, at);
+        take_better(far_cost, far_len, c + 3 + e, at - (b + i));
+        lo = hi + 1;
+      }
+    }
+
+    // ------------------------------ near phase: 32 sequential positions, high to low
+    uint32_t cur = 0;                                            // cost of this lane's position
+    uint32_t keep = 1;
+    for (int32_t l = 31; l >= 0; l--)
+    {
+      const uint32_t pos = i0 + (uint32_t)l;
+      const uint32_t Ml = __shfl_sync(0xffffffffu, M, l);
+      const uint32_t fc = __shfl_sync(0xffffffffu, far_cost, l);
+      const uint32_t fl = __shfl_sync(0xffffffffu, far_len, l);
+      const uint32_t fz = __shfl_sync(0xffffffffu, (uint32_t)forced, l);
+      // candidates held in registers: this group (length lane-l) and the next one (length 32+lane-l)
+      uint32_t key = 0xffffffffu;
+      {
+        const int32_t L1 = (int32_t)lane - l;
+        const uint32_t L2 = (uint32_t)(L1 + 32);
+        if (L1 >= (int32_t)kMinMatch && (uint32_t)L1 <= Ml)
+          key = ((cur + 3 + ((uint32_t)L1 >= 19 ? 1u : 0u)) << 6) | (63u - (uint32_t)L1);
+        if (L2 >= kMinMatch && L2 <= Ml)
+        {
+          uint32_t k2 = ((prv + 3 + (L2 >= 19 ? 1u : 0u)) << 6) | (63u - L2);
+          key = min(key, k2);
+        }
+      }
+      const uint32_t best = __reduce_min_sync(0xffffffffu, key);
+      if (pos > last_priced) continue;                           // uniform
+
+      run++;
+      uint32_t lowest = next_cost + 1;
+      if (run == 15 || (run >= 15 + 255 && (run - 15) % 255 == 0)) lowest++;
+      uint32_t choice = 1;
+      if (fz) { lowest = fc; choice = fl; }
+      else
+      {
+        uint32_t mc = 0xffffffffu, ml = 0;
+        if (best != 0xffffffffu) { mc = best >> 6; ml = 63u - (best & 63u); }
+        take_better(mc, ml, fc, fl);
+        if (ml != 0 && mc <= lowest) { lowest = mc; choice = ml; }
+      }
+      if (choice != 1) run = 0;
+      next_cost = lowest;
+      if (lane == (uint32_t)l) { cur = lowest; keep = choice; }
+    }
+
+    // ------------------------------ publish the group: costs, final lengths, sparse-table levels
+    if (i < n)
+    {
+      s.cost[b + i] = cur;
+      if (priced) mlen[b + i] = keep;
+    }
+    // st5: min over cost[i .. i+31] = suffix of this group from `lane` + prefix of the next group below `lane`
+    uint32_t kc = (cur << 6) | (63u - lane);                     // index lane      (this group)
+    uint32_t kp = (prv << 6) | (31u - lane);                     // index 32 + lane (next group)
+#pragma unroll
+    for (uint32_t d = 1; d < 32; d <<= 1)
+    {
+      uint32_t t = __shfl_down_sync(0xffffffffu, kc, d);
+      if (lane + d < 32) kc = min(kc, t);
+      uint32_t u = __shfl_up_sync(0xffffffffu, kp, d);
+      if (lane >= d) kp = min(kp, u);
+    }
+    uint32_t kp_excl = __shfl_up_sync(0xffffffffu, kp, 1);
+    if (lane == 0) kp_excl = 0xffffffffu;
+    const uint32_t k5 = min(kc, kp_excl);
+    const uint32_t off5 = (63u - (k5 & 63u)) - lane;             // 0..31
+    const uint32_t v5 = ((k5 >> 6) << 8) | (255u - off5);
+    // st6 = st5[i] (+) st5[i+32] ; st7 = st6[i] (+) st6[i+64]; the later window wins ties
+    uint32_t v6 = v5;
+    if (p5 != 0xffffffffu && (p5 >> 8) <= (v5 >> 8)) v6 = ((p5 >> 8) << 8) | ((p5 & 255u) - 32u);
+    uint32_t v7 = v6;
+    if (p6b != 0xffffffffu && (p6b >> 8) <= (v6 >> 8)) v7 = ((p6b >> 8) << 8) | ((p6b & 255u) - 64u);
+    if (i < n) { s.st5[b + i] = v5; s.st6[b + i] = v6; s.st7[b + i] = v7; }
+    p6b = p6a; p6a = v6; p5 = v5;
+    prv = cur;
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Walk the chosen parse from the start of the block and list its sequences.
+// record = { position of the match, match length (0 = final literals), distance, offset of the
+// sequence inside the compressed block }.  The literals of a sequence start where the previous
+// record's match ended.
+// ---------------------------------------------------------------------------------------------
+struct SeqRec { uint32_t pos, len, dist, out; };
+
+__device__ __forceinline__ uint32_t seq_bytes(uint32_t lits, uint32_t len, bool last)
+{
+  uint32_t sz = 1 + len_ext_bytes(lits) + lits;
+  if (!last)
+  {
+    sz += 2;
+    if (len >= kMinMatch + 15) sz += 1 + (len - kMinMatch - 15) / 255;
+  }
+  return sz;
+}
+
+__global__ void __launch_bounds__(32)
+k_path(const uint32_t* mlen, const uint16_t* mdist, SeqRec* seqs, uint32_t seq_stride, uint32_t* seq_count,
+       uint32_t* packed_size, Geom g)
+{
+  const uint32_t j = blockIdx.x;
+  if (j >= g.n_blocks) return;
+  const uint32_t b = block_begin(g, j), n = block_len(g, j);
+  const uint32_t lane = threadIdx.x;
+  SeqRec* out = seqs + (size_t)j * seq_stride;
+
+  uint32_t at = 0;            // current position on the path (block relative)
+  uint32_t lit_from = 0;      // start of the pending literals
+  uint32_t bytes = 0, count = 0;
+  while (at < n)
+  {
+    const uint32_t w = at & ~31u;
+    uint32_t L = 0, Dd = 0;
+    if (w + lane < n) { L = mlen[b + w + lane]; Dd = mdist[b + w + lane]; }
+    uint32_t is_match = __ballot_sync(0xffffffffu, L > 1);
+    uint32_t o = at - w;
+    while (o < 32)
+    {
+      uint32_t m = is_match & ~((o == 0) ? 0u : ((1u << o) - 1u));
+      if (m == 0) { o = 32; at = w + 32; break; }
+      const int ml = __ffs((int)m) - 1;
+      const uint32_t len = __shfl_sync(0xffffffffu, L, ml);
+      const uint32_t dist = __shfl_sync(0xffffffffu, Dd, ml);
+      const uint32_t pos = w + (uint32_t)ml;
+      if (lane == 0) { SeqRec r; r.pos = pos; r.len = len; r.dist = dist; r.out = bytes; out[count] = r; }
+      bytes += seq_bytes(pos - lit_from, len, false);
+      count++;
+      at = pos + len;
+      lit_from = at;
+      o = at - w;                      // may be >= 32: leaves the window
+    }
+  }
+  // final literals (smallz4.h:292-308: the last token has no match)
+  if (lane == 0) { SeqRec r; r.pos = n; r.len = 0; r.dist = 0; r.out = bytes; out[count] = r; }
+  bytes += seq_bytes(n - lit_from, 0, true);
+  count++;
+  if (lane == 0) { seq_count[j] = count; packed_size[j] = bytes; }
+}
+
+}  // namespace sz4

@@ -1,0 +1,565 @@
+// sz4_pipeline.cu -- host side of libsmallz4_b200.so: device buffers, the per-batch kernel sequence,
+// frame assembly and the C ABI (include/smallz4_b200.h).
+//
+// Reference control flow being replaced: smallz4::compress(), smallz4.h:476-814.  The reference
+// runs three phases per 4 MiB block, sequentially; here a batch of blocks runs each phase as one
+// or a few grid-wide launches (DESIGN.md has the kernel table).  There is no CPU implementation of
+// any phase in this library: without a CUDA device every entry point returns SZ4_ERR_CUDA.
+#include "sz4_platform.h"
+#include "sz4_device.cuh"
+#include "sz4_sort.cuh"
+#include "sz4_chain.cuh"
+#include "sz4_search.cuh"
+#include "sz4_parse.cuh"
+#include "sz4_emit.cuh"
+#include "sz4_scalar.cuh"
+
+#include "../../include/smallz4_b200.h"
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+using namespace sz4;
+
+namespace
+{
+const uint32_t kBlockModern = 4u << 20;     // smallz4.h:124
+const uint32_t kBlockLegacy = 8u << 20;     // smallz4.h:127
+const uint32_t kHaloBytes   = 131072;       // >= 65535 + 12, keeps block starts 16-byte aligned
+
+struct DevBuf
+{
+  void*  p = nullptr;
+  size_t bytes = 0;
+};
+}  // namespace
+
+struct sz4_ctx
+{
+  int          device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t  ev0 = nullptr, ev1 = nullptr;
+  std::string  err;
+  // options
+  uint32_t batch_blocks = 64;
+  uint32_t block_size_override = 0;
+  int      stage_bulk = 1;
+  int      debug_keep = 0;
+  int      force_scalar = 0;
+  // device memory (grow-only)
+  DevBuf data, ph, pe, mlen, mdist, scratch, hist, hist_scanned, partials, seqs, seq_count, packed,
+         saved_ph, saved_pe, seeds, nseeds, seg, block_out, seg_total, dbg_len, dbg_dist, scalar_state;
+  unsigned long long* h_seg_total = nullptr;    // pinned
+  // stats
+  double             kernel_ms = 0;
+  unsigned long long launches = 0;
+  Geom               last_geom;
+  bool               attr_set = false;
+
+  int fail(const char* what, cudaError_t e)
+  {
+    err = std::string(what) + ": " + cudaGetErrorString(e);
+    return SZ4_ERR_CUDA;
+  }
+};
+
+#define CK(call)                                               \
+  do {                                                         \
+    cudaError_t e_ = (call);                                   \
+    if (e_ != cudaSuccess) return ctx->fail(#call, e_);        \
+  } while (0)
+
+#define LAUNCH(ctx, kernel, grid, block, smem, ...)                        \
+  do {                                                                     \
+    SZ4_LAUNCH(kernel, grid, block, smem, (ctx)->stream, __VA_ARGS__);     \
+    (ctx)->launches++;                                                     \
+  } while (0)
+
+static int reserve(sz4_ctx* ctx, DevBuf& b, size_t bytes)
+{
+  if (b.bytes >= bytes) return SZ4_OK;
+  if (b.p) { CK(cudaFree(b.p)); b.p = nullptr; b.bytes = 0; }
+  size_t want = bytes + bytes / 8 + 4096;
+  cudaError_t e = cudaMalloc(&b.p, want);
+  if (e != cudaSuccess) { b.p = nullptr; ctx->err = "cudaMalloc failed"; return SZ4_ERR_NOMEM; }
+  b.bytes = want;
+  return SZ4_OK;
+}
+#define RSV(buf, bytes) do { int r_ = reserve(ctx, ctx->buf, (bytes)); if (r_ != SZ4_OK) return r_; } while (0)
+
+static uint32_t div_up(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
+
+// exclusive scan of n uint32 on the device (in -> out)
+static int device_scan(sz4_ctx* ctx, const uint32_t* in, uint32_t* out, uint32_t n)
+{
+  uint32_t chunks = div_up(n, kScanChunk);
+  RSV(partials, (size_t)chunks * 4 + 64);
+  uint32_t* part = (uint32_t*)ctx->partials.p;
+  LAUNCH(ctx, k_scan_reduce, chunks, kScanThreads, 0, in, n, part);
+  LAUNCH(ctx, k_scan_partials, 1, kScanThreads, 0, part, chunks);
+  LAUNCH(ctx, k_scan_apply, chunks, kScanThreads, 0, in, out, n, (const uint32_t*)part);
+  return SZ4_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// One batch: ctx->data holds kPad zero bytes, g.n_total input bytes, zero padding.  Produces the
+// concatenated block records in ctx->seg and their total size in *ctx->h_seg_total (after a sync).
+// ---------------------------------------------------------------------------------------------
+static int run_batch(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
+{
+  const uint32_t N = g.n_total;
+  uint8_t* data = (uint8_t*)ctx->data.p + kPad;
+
+  RSV(ph, ((size_t)N + 2 * kPad) * 2);
+  RSV(pe, ((size_t)N + 2 * kPad) * 2);
+  RSV(mlen, ((size_t)N + kPad) * 4);
+  RSV(mdist, ((size_t)N + kPad) * 2);
+  RSV(scratch, ((size_t)N + kPad) * 16 + 256);
+  RSV(saved_ph, (size_t)g.n_blocks * 4 + 64);
+  RSV(saved_pe, (size_t)g.n_blocks * 4 + 64);
+  RSV(seq_count, (size_t)g.n_blocks * 4 + 64);
+  RSV(packed, (size_t)g.n_blocks * 4 + 64);
+  RSV(block_out, (size_t)g.n_blocks * sizeof(BlockOut) + 64);
+  RSV(seg_total, 64);
+  RSV(nseeds, 64);
+  const uint32_t max_seeds = N / 65000 + g.n_blocks + 16;
+  RSV(seeds, (size_t)max_seeds * sizeof(Seed));
+  // a sequence ends with a match of >= 4 bytes (>= 2 with a dictionary, DESIGN.md Q-dict)
+  const uint32_t seq_stride = g.block_size / (g.shift ? 2 : 4) + 8;
+  RSV(seqs, (size_t)g.n_blocks * seq_stride * sizeof(SeqRec));
+  const uint64_t per_block_out = g.legacy ? (uint64_t)g.block_size + g.block_size / 255 + 64 : (uint64_t)g.block_size;
+  const uint64_t seg_cap = (uint64_t)g.n_blocks * (per_block_out + 4) + 64;
+  RSV(seg, seg_cap);
+
+  uint16_t* ph = (uint16_t*)ctx->ph.p + kPad;
+  uint16_t* pe = (uint16_t*)ctx->pe.p + kPad;
+  uint32_t* mlen = (uint32_t*)ctx->mlen.p;
+  uint16_t* mdist = (uint16_t*)ctx->mdist.p;
+  uint32_t* saved_ph = (uint32_t*)ctx->saved_ph.p;
+  uint32_t* saved_pe = (uint32_t*)ctx->saved_pe.p;
+
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  CK(cudaMemsetAsync(ctx->ph.p, 0, ((size_t)N + 2 * kPad) * 2, ctx->stream));
+  CK(cudaMemsetAsync(ctx->pe.p, 0, ((size_t)N + 2 * kPad) * 2, ctx->stream));
+  CK(cudaMemsetAsync(mlen, 0, (size_t)N * 4, ctx->stream));
+  CK(cudaMemsetAsync(mdist, 0, (size_t)N * 2, ctx->stream));
+
+  if (scalar_finder)
+  {
+    // dictionary stream with runs long enough for the reference's long-run shortcut: the ring
+    // semantics are replayed literally by one thread (sz4_scalar.cuh; DESIGN.md Q-dict)
+    RSV(scalar_state, (sizeof(uint64_t) << kHashBits) + 2 * 65536 * sizeof(uint16_t));
+    CK(cudaMemsetAsync(ctx->scalar_state.p, 0xff, sizeof(uint64_t) << kHashBits, ctx->stream));
+    LAUNCH(ctx, k_scalar_find, 1, 32, 0, (const uint8_t*)data, (unsigned long long*)ctx->scalar_state.p, ph, pe, mlen, mdist, g);
+  }
+  else
+  {
+    // ---- phase 1: previous occurrence of every position's hash (sort) and exact chains
+    const uint32_t first = g.first_ins;
+    const uint32_t count = N >= first + 4 ? N - 3 - first : 0;
+    if (count > 0)
+    {
+      uint64_t* bufA = (uint64_t*)ctx->scratch.p;
+      uint64_t* bufB = bufA + (((size_t)N + kPad + 1) & ~(size_t)1);
+      const uint32_t tiles = div_up(count, kSortTile);
+      const uint32_t hist_n = tiles * kSortBins;
+      RSV(hist, (size_t)hist_n * 4 + 64);
+      RSV(hist_scanned, (size_t)hist_n * 4 + 64);
+      uint32_t* hist = (uint32_t*)ctx->hist.p;
+      uint32_t* hscan = (uint32_t*)ctx->hist_scanned.p;
+      const uint32_t shifts[3] = { 0, 7, 14 }, masks[3] = { 127, 127, 63 };
+      uint64_t* src = nullptr;
+      uint64_t* dst = bufA;
+      for (int pass = 0; pass < 3; pass++)
+      {
+        if (pass == 0)
+          LAUNCH(ctx, k_sort_hist<true>, tiles, kSortThreads, 0, (const uint64_t*)nullptr, (const uint8_t*)data, first, count, shifts[0], masks[0], hist, tiles);
+        else
+          LAUNCH(ctx, k_sort_hist<false>, tiles, kSortThreads, 0, (const uint64_t*)src, (const uint8_t*)data, first, count, shifts[pass], masks[pass], hist, tiles);
+        int r = device_scan(ctx, hist, hscan, hist_n);
+        if (r != SZ4_OK) return r;
+        if (pass == 0)
+          LAUNCH(ctx, k_sort_scatter<true>, tiles, kSortThreads, 0, (const uint64_t*)nullptr, dst, (const uint8_t*)data, first, count, shifts[0], masks[0], (const uint32_t*)hscan, tiles);
+        else
+          LAUNCH(ctx, k_sort_scatter<false>, tiles, kSortThreads, 0, (const uint64_t*)src, dst, (const uint8_t*)data, first, count, shifts[pass], masks[pass], (const uint32_t*)hscan, tiles);
+        src = dst;
+        dst = (dst == bufA) ? bufB : bufA;
+      }
+      LAUNCH(ctx, k_link, div_up(count, 256), 256, 0, (const uint64_t*)src, count, ph, g);
+      LAUNCH(ctx, k_twice_save, div_up(g.n_blocks, 64), 64, 0, ph, saved_ph, g);
+      LAUNCH(ctx, k_exact_walk, div_up(count, 256), 256, 0, (const uint8_t*)data, (const uint16_t*)ph, (const uint32_t*)saved_ph, pe, first, count, g);
+      LAUNCH(ctx, k_twice_save, div_up(g.n_blocks, 64), 64, 0, pe, saved_pe, g);
+
+      // ---- phase 2: longest match per position
+      const uint32_t tiles_per_block = div_up(g.block_size, kTile);
+      if (!ctx->attr_set)
+      {
+        CK(cudaFuncSetAttribute(k_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSearchSmem));
+        ctx->attr_set = true;
+      }
+      LAUNCH(ctx, k_search, g.n_blocks * tiles_per_block, kSearchThreads, kSearchSmem, (const uint8_t*)data, (const uint16_t*)pe,
+             (const uint32_t*)saved_pe, mlen, mdist, tiles_per_block, g, ctx->stage_bulk);
+      if (g.max_chain <= kLazyMax)
+        LAUNCH(ctx, k_greedy_filter, div_up(g.n_blocks, 32), 32, 0, (const uint8_t*)data, (const uint16_t*)pe, (const uint32_t*)saved_pe, mlen, mdist, g);
+      else
+      {
+        CK(cudaMemsetAsync(ctx->nseeds.p, 0, 4, ctx->stream));
+        LAUNCH(ctx, k_seed_detect, div_up(N - g.halo, 256), 256, 0, (const uint8_t*)data, (const uint32_t*)mlen, (const uint16_t*)mdist,
+               (Seed*)ctx->seeds.p, (uint32_t*)ctx->nseeds.p, max_seeds, g);
+        LAUNCH(ctx, k_seed_fix, max_seeds, 256, 0, mlen, mdist, (const Seed*)ctx->seeds.p, (const uint32_t*)ctx->nseeds.p, g);
+      }
+    }
+  }
+
+  if (ctx->debug_keep)
+  {
+    RSV(dbg_len, (size_t)N * 4 + 64);
+    RSV(dbg_dist, (size_t)N * 2 + 64);
+    CK(cudaMemcpyAsync(ctx->dbg_len.p, mlen, (size_t)N * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->dbg_dist.p, mdist, (size_t)N * 2, cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+
+  // ---- phase 3: cost DP (levels > 3), parse walk, emission
+  DpScratch dp;
+  dp.cost = (uint32_t*)ctx->scratch.p;
+  dp.st5 = dp.cost + N + 64;
+  dp.st6 = dp.st5 + N + 64;
+  dp.st7 = dp.st6 + N + 64;
+  if (g.max_chain > kGreedyMax)                                   // smallz4.h:755
+    LAUNCH(ctx, k_dp, g.n_blocks, 32, 0, mlen, (const uint16_t*)mdist, dp, g);
+  LAUNCH(ctx, k_path, g.n_blocks, 32, 0, (const uint32_t*)mlen, (const uint16_t*)mdist, (SeqRec*)ctx->seqs.p, seq_stride,
+         (uint32_t*)ctx->seq_count.p, (uint32_t*)ctx->packed.p, g);
+  LAUNCH(ctx, k_block_offsets, 1, 32, 0, (const uint32_t*)ctx->packed.p, (BlockOut*)ctx->block_out.p,
+         (unsigned long long*)ctx->seg_total.p, (uint8_t*)ctx->seg.p, g);
+  const uint32_t chunks = div_up(per_block_out / 16 + 2, 256);
+  LAUNCH(ctx, k_emit, g.n_blocks * chunks, 256, 0, (const uint8_t*)data, (const SeqRec*)ctx->seqs.p, seq_stride,
+         (const uint32_t*)ctx->seq_count.p, (const BlockOut*)ctx->block_out.p, (uint8_t*)ctx->seg.p, chunks, g);
+  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->h_seg_total, ctx->seg_total.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaGetLastError());
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  ctx->kernel_ms += ms;
+  ctx->last_geom = g;
+  return SZ4_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stream driver: cuts [prefix | input] into batches of whole blocks with their halo
+// ---------------------------------------------------------------------------------------------
+struct StreamJob
+{
+  const uint8_t* src = nullptr;     // halo_in_src bytes of history, then n bytes of blocks
+  bool   src_on_device = false;
+  size_t halo_in_src = 0;
+  size_t n = 0;
+  bool   first = true, last = true;
+  const uint8_t* dict = nullptr;    // only with first
+  size_t dict_len = 0;
+  uint8_t* dst = nullptr;
+  bool   dst_on_device = false;
+  size_t cap = 0;
+  uint32_t max_chain = 65535;
+  bool   legacy = false;
+};
+
+static bool has_long_run(const uint8_t* p, size_t n, size_t limit)
+{
+  size_t run = 1;
+  for (size_t i = 1; i < n; i++)
+  {
+    if (p[i] == p[i - 1]) { if (++run >= limit) return true; }
+    else run = 1;
+  }
+  return false;
+}
+
+static int compress_blocks(sz4_ctx* ctx, const StreamJob& job, size_t* out_len)
+{
+  const uint32_t bs = ctx->block_size_override ? ctx->block_size_override : (job.legacy ? kBlockLegacy : kBlockModern);
+  if (bs % 65536 != 0 || bs < 131072) { ctx->err = "block_size must be a multiple of 65536 and >= 131072"; return SZ4_ERR_ARG; }
+  const cudaMemcpyKind in_kind = job.src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  const cudaMemcpyKind out_kind = job.dst_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+
+  // dictionary prefix (smallz4.h:554-570; the CLI keeps the last 65536 bytes, smallz4.cpp:291-302)
+  std::vector<uint8_t> prefix;
+  uint32_t first_ins = 0;
+  const uint8_t* dict = job.dict;
+  size_t dict_len = job.first && dict ? job.dict_len : 0;
+  if (dict_len > 65536) { dict += dict_len - 65536; dict_len = 65536; }
+  const bool with_dict = dict_len > 0;
+  if (with_dict)
+  {
+    if (job.legacy) { ctx->err = "legacy format does not support dictionaries"; return SZ4_ERR_ARG; }   // smallz4.cpp:275
+    if (job.src_on_device) { ctx->err = "dictionaries are supported through the host entry points only"; return SZ4_ERR_ARG; }
+    prefix.assign(kWindow, 0);
+    size_t keep = dict_len < (size_t)kWindow ? dict_len : (size_t)kWindow;
+    memcpy(prefix.data() + kWindow - keep, dict + dict_len - keep, keep);
+    first_ins = dict_len >= 65536 ? 0 : (uint32_t)(kWindow - keep);
+  }
+  bool scalar = false;
+  if (with_dict)
+  {
+    // the parallel finder is exact for dictionary streams only while the long-run shortcut
+    // (smallz4.h:632) cannot fire; otherwise one thread replays the reference's ring literally
+    scalar = ctx->force_scalar || has_long_run(job.src, job.n, 65280) || has_long_run(prefix.data(), prefix.size(), 60000);
+  }
+
+  const uint64_t blocks_total = (job.n + bs - 1) / bs;
+  uint32_t per_batch = ctx->batch_blocks ? ctx->batch_blocks : 64;
+  const uint64_t max_batch_bytes = 1ull << 30;
+  if ((uint64_t)per_batch * bs > max_batch_bytes) per_batch = (uint32_t)(max_batch_bytes / bs);
+  if (scalar) per_batch = (uint32_t)blocks_total;                 // ring state lives in one launch
+  if (scalar && job.n + kWindow > max_batch_bytes) { ctx->err = "dictionary stream with long runs is limited to 1 GiB"; return SZ4_ERR_ARG; }
+
+  size_t o = 0;
+  for (uint64_t kb = 0; kb < blocks_total; kb += per_batch)
+  {
+    const uint64_t ke = kb + per_batch < blocks_total ? kb + per_batch : blocks_total;
+    const size_t pay_lo = (size_t)(kb * bs);
+    const size_t pay_hi = (size_t)(ke * bs) < job.n ? (size_t)(ke * bs) : job.n;
+    const bool batch_first = job.first && kb == 0;
+    size_t halo;
+    if (batch_first) halo = with_dict ? kWindow : 0;
+    else if (job.legacy) halo = 0;
+    else
+    {
+      size_t avail = pay_lo + job.halo_in_src;                     // history present in src
+      halo = avail < kHaloBytes ? avail : kHaloBytes;
+    }
+    Geom g;
+    memset(&g, 0, sizeof(g));
+    g.halo = (uint32_t)halo;
+    g.n_total = (uint32_t)(halo + (pay_hi - pay_lo));
+    g.block_size = bs;
+    g.n_blocks = (uint32_t)(ke - kb);
+    g.first_ins = batch_first ? first_ins : 0;
+    g.max_chain = job.max_chain;
+    g.shift = with_dict ? 1 : 0;
+    g.legacy = job.legacy ? 1 : 0;
+    g.stream_first = batch_first ? 1 : 0;
+    g.stream_last = (job.last && ke == blocks_total) ? 1 : 0;
+
+    RSV(data, (size_t)g.n_total + 2 * kPad + 64);
+    uint8_t* d = (uint8_t*)ctx->data.p;
+    CK(cudaMemsetAsync(d, 0, kPad, ctx->stream));
+    CK(cudaMemsetAsync(d + kPad + g.n_total, 0, kPad + 64, ctx->stream));
+    if (batch_first && with_dict)
+    {
+      CK(cudaMemcpyAsync(d + kPad, prefix.data(), kWindow, cudaMemcpyHostToDevice, ctx->stream));
+      CK(cudaMemcpyAsync(d + kPad + kWindow, job.src + job.halo_in_src + pay_lo, pay_hi - pay_lo, in_kind, ctx->stream));
+    }
+    else
+      CK(cudaMemcpyAsync(d + kPad, job.src + job.halo_in_src + pay_lo - halo, halo + (pay_hi - pay_lo), in_kind, ctx->stream));
+
+    int r = run_batch(ctx, g, scalar);
+    if (r != SZ4_OK) return r;
+    const size_t seg_len = (size_t)*ctx->h_seg_total;
+    if (o + seg_len > job.cap) { ctx->err = "destination too small"; return SZ4_ERR_DST_SMALL; }
+    CK(cudaMemcpyAsync(job.dst + o, ctx->seg.p, seg_len, out_kind, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    o += seg_len;
+  }
+  *out_len = o;
+  return SZ4_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* sz4_version(void) { return "1.5-b200.1"; }
+
+int sz4_create(sz4_ctx** out, int device)
+{
+  if (!out) return SZ4_ERR_ARG;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0)
+  {
+    fprintf(stderr, "smallz4_b200: no usable CUDA device (%s); this library has no CPU path\n",
+            e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    return SZ4_ERR_CUDA;
+  }
+  sz4_ctx* ctx = new sz4_ctx();
+  if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
+  ctx->device = device;
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
+      cudaMallocHost((void**)&ctx->h_seg_total, 64) != cudaSuccess)
+  {
+    fprintf(stderr, "smallz4_b200: cannot initialise CUDA device %d\n", device);
+    delete ctx;
+    return SZ4_ERR_CUDA;
+  }
+  *out = ctx;
+  return SZ4_OK;
+}
+
+void sz4_destroy(sz4_ctx* ctx)
+{
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  DevBuf* all[] = { &ctx->data, &ctx->ph, &ctx->pe, &ctx->mlen, &ctx->mdist, &ctx->scratch, &ctx->hist, &ctx->hist_scanned,
+                    &ctx->partials, &ctx->seqs, &ctx->seq_count, &ctx->packed, &ctx->saved_ph, &ctx->saved_pe, &ctx->seeds,
+                    &ctx->nseeds, &ctx->seg, &ctx->block_out, &ctx->seg_total, &ctx->dbg_len, &ctx->dbg_dist, &ctx->scalar_state };
+  for (DevBuf* b : all) if (b->p) cudaFree(b->p);
+  if (ctx->h_seg_total) cudaFreeHost(ctx->h_seg_total);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* sz4_last_error(const sz4_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context"; }
+
+int sz4_set_option(sz4_ctx* ctx, const char* name, long long value)
+{
+  if (!ctx || !name) return SZ4_ERR_ARG;
+  if (!strcmp(name, "batch_blocks")) { if (value < 1) return SZ4_ERR_ARG; ctx->batch_blocks = (uint32_t)value; return SZ4_OK; }
+  if (!strcmp(name, "block_size")) { ctx->block_size_override = (uint32_t)value; return SZ4_OK; }
+  if (!strcmp(name, "stage_bulk")) { ctx->stage_bulk = value != 0; return SZ4_OK; }
+  if (!strcmp(name, "debug_keep")) { ctx->debug_keep = value != 0; return SZ4_OK; }
+  if (!strcmp(name, "force_scalar")) { ctx->force_scalar = value != 0; return SZ4_OK; }
+  ctx->err = "unknown option";
+  return SZ4_ERR_ARG;
+}
+
+size_t sz4_compress_bound(size_t n, int use_legacy_format)
+{
+  // modern: a block is stored when packing does not shrink it; legacy blocks are always packed
+  size_t bs = use_legacy_format ? kBlockLegacy : kBlockModern;
+  size_t blocks = n / bs + 1;
+  size_t worst = use_legacy_format ? n + n / 255 + 64 * blocks : n;
+  return worst + 4 * blocks + 16;
+}
+
+size_t sz4_frame_header(unsigned char* dst, int use_legacy_format)
+{
+  if (use_legacy_format) { const unsigned char h[4] = { 0x02, 0x21, 0x4C, 0x18 }; memcpy(dst, h, 4); return 4; }   // smallz4.h:482
+  const unsigned char h[7] = { 0x04, 0x22, 0x4D, 0x18, 1 << 6, 7 << 4, 0xDF };                                     // smallz4.h:488-494
+  memcpy(dst, h, 7);
+  return 7;
+}
+
+size_t sz4_frame_end(unsigned char* dst, int use_legacy_format)
+{
+  if (use_legacy_format) return 0;
+  memset(dst, 0, 4);                                                                                               // smallz4.h:809-813
+  return 4;
+}
+
+int sz4_compress_host(sz4_ctx* ctx, const void* src, size_t n, void* dst, size_t cap, size_t* frame_len,
+                      unsigned short max_chain, const unsigned char* dict, size_t dict_len, int legacy)
+{
+  if (!ctx || (!src && n) || !dst || !frame_len) return SZ4_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  ctx->kernel_ms = 0; ctx->launches = 0;
+  uint8_t* out = (uint8_t*)dst;
+  if (cap < 16) { ctx->err = "destination too small"; return SZ4_ERR_DST_SMALL; }
+  size_t o = sz4_frame_header(out, legacy);
+
+  if (max_chain == 0)
+  {
+    // level -0 (smallz4.h:511,765-780): blocks are stored; nothing to compute.  Legacy frames
+    // cannot mark stored blocks, the reference then writes empty blocks -- so do we.
+    const size_t bs = ctx->block_size_override ? ctx->block_size_override : (legacy ? kBlockLegacy : kBlockModern);
+    for (size_t at = 0; at < n; at += bs)
+    {
+      size_t len = n - at < bs ? n - at : bs;
+      uint32_t tagged = legacy ? 0u : ((uint32_t)len | 0x80000000u);
+      size_t body = legacy ? 0 : len;
+      if (o + 4 + body + 4 > cap) { ctx->err = "destination too small"; return SZ4_ERR_DST_SMALL; }
+      out[o++] = (uint8_t)tagged; out[o++] = (uint8_t)(tagged >> 8); out[o++] = (uint8_t)(tagged >> 16); out[o++] = (uint8_t)(tagged >> 24);
+      memcpy(out + o, (const uint8_t*)src + at, body);
+      o += body;
+    }
+  }
+  else
+  {
+    StreamJob job;
+    job.src = (const uint8_t*)src; job.n = n; job.dict = dict; job.dict_len = dict_len;
+    job.dst = out + o; job.cap = cap - o - 4; job.max_chain = max_chain; job.legacy = legacy != 0;
+    size_t seg = 0;
+    int r = compress_blocks(ctx, job, &seg);
+    if (r != SZ4_OK) return r;
+    o += seg;
+  }
+  if (o + 4 > cap) { ctx->err = "destination too small"; return SZ4_ERR_DST_SMALL; }
+  o += sz4_frame_end(out + o, legacy);
+  *frame_len = o;
+  return SZ4_OK;
+}
+
+int sz4_compress_device(sz4_ctx* ctx, const void* d_src, size_t halo, size_t n, int is_first, int is_last,
+                        void* d_dst, size_t cap, size_t* segment_len, unsigned short max_chain, int legacy, void* cuda_stream)
+{
+  if (!ctx || !d_src || !d_dst || !segment_len || max_chain == 0) return SZ4_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  (void)cuda_stream;   // work is ordered on the context's stream; the caller's stream is synchronised by the blocking return
+  ctx->kernel_ms = 0; ctx->launches = 0;
+  StreamJob job;
+  job.src = (const uint8_t*)d_src; job.src_on_device = true; job.halo_in_src = halo; job.n = n;
+  job.first = is_first != 0; job.last = is_last != 0;
+  job.dst = (uint8_t*)d_dst; job.dst_on_device = true; job.cap = cap; job.max_chain = max_chain; job.legacy = legacy != 0;
+  if (job.first && halo != 0) { ctx->err = "the first block of a stream has no halo"; return SZ4_ERR_ARG; }
+  return compress_blocks(ctx, job, segment_len);
+}
+
+int sz4_lz4(sz4_ctx* ctx, sz4_get_bytes get_bytes, sz4_send_bytes send_bytes, unsigned short max_chain,
+            const unsigned char* dict, size_t dict_len, int legacy, void* user)
+{
+  if (!ctx || !get_bytes || !send_bytes) return SZ4_ERR_ARG;
+  // pull the stream in 64 KiB requests like the reference (smallz4.h:577, BufferSize)
+  std::vector<uint8_t> in;
+  const size_t kChunk = 64 * 1024;
+  for (;;)
+  {
+    size_t at = in.size();
+    in.resize(at + kChunk);
+    size_t got = get_bytes(in.data() + at, kChunk, user);
+    in.resize(at + got);
+    if (got == 0) break;
+  }
+  size_t cap = sz4_compress_bound(in.size(), legacy) + (dict_len ? in.size() : 0);
+  std::vector<uint8_t> out(cap);
+  size_t len = 0;
+  int r = sz4_compress_host(ctx, in.data(), in.size(), out.data(), cap, &len, max_chain, dict, dict_len, legacy);
+  if (r != SZ4_OK) return r;
+  send_bytes(out.data(), len, user);
+  return SZ4_OK;
+}
+
+int sz4_last_stats(const sz4_ctx* ctx, double* kernel_ms, unsigned long long* launches)
+{
+  if (!ctx) return SZ4_ERR_ARG;
+  if (kernel_ms) *kernel_ms = ctx->kernel_ms;
+  if (launches) *launches = ctx->launches;
+  return SZ4_OK;
+}
+
+int sz4_debug_fetch(sz4_ctx* ctx, const char* what, void* dst, size_t count)
+{
+  if (!ctx || !what || !dst) return SZ4_ERR_ARG;
+  const Geom& g = ctx->last_geom;
+  if (count > g.n_total) count = g.n_total;
+  const void* src = nullptr; size_t elem = 0;
+  if (!strcmp(what, "pe")) { src = (uint16_t*)ctx->pe.p + kPad; elem = 2; }
+  else if (!strcmp(what, "ph")) { src = (uint16_t*)ctx->ph.p + kPad; elem = 2; }
+  else if (!strcmp(what, "len_found")) { src = ctx->dbg_len.p; elem = 4; }
+  else if (!strcmp(what, "dist_found")) { src = ctx->dbg_dist.p; elem = 2; }
+  else if (!strcmp(what, "len_final")) { src = ctx->mlen.p; elem = 4; }
+  else if (!strcmp(what, "dist_final")) { src = ctx->mdist.p; elem = 2; }
+  else if (!strcmp(what, "cost")) { src = ctx->scratch.p; elem = 4; }
+  if (!src) { ctx->err = "unknown array"; return SZ4_ERR_ARG; }
+  CK(cudaMemcpy(dst, src, count * elem, cudaMemcpyDeviceToHost));
+  return SZ4_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,343 @@
+// sz4_search.cuh -- phase 2: longest match for every position (smallz4.h:173 findLongestMatch).
+//
+// One CTA per tile of kTile positions.  The CTA stages its slice of the input plus the 64 KiB of
+// history in front of it, and the previousExact entries of the same range, into shared memory
+// (cp.async.bulk -> SASS UBLKCP, completion on an mbarrier), then every lane walks the exact
+// chain of one position at a time.  Lanes that finish pull the next position of the tile
+// (persistent lanes) so that short and long chains mix inside a warp.
+//
+// The walk is a literal restatement of the reference loop, including what it does NOT check:
+// the first candidate is accepted without comparing bytes 0..1, later ones without byte 0
+// (harmless without a dictionary because chain members share their first four bytes; with a
+// dictionary the shifted ring makes it visible, DESIGN.md Q-dict).  Result: longest match,
+// nearest candidate on ties, at most max_chain improvements.
+#pragma once
+#include "sz4_device.cuh"
+
+namespace sz4
+{
+enum : uint32_t
+{
+  kTile          = 8192,     // positions per CTA
+  kLook          = 3584,     // bytes staged behind the tile for match extension
+  kHist          = 65536,    // history staged in front of the tile
+  kSearchThreads = 512,
+  kDataBytes     = kHist + kTile + kLook + 16,
+  kChainElems    = kHist + 16 + kTile,
+  kSearchSmem    = kDataBytes + 2 * kChainElems
+};
+
+#ifndef SZ4_EMU
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "SZ4_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra SZ4_DONE_%=;\n"
+      "bra SZ4_WAIT_%=;\n"
+      "SZ4_DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+#endif
+
+// Copy two global ranges into shared memory.  Sizes and addresses are multiples of 16.
+__device__ __forceinline__ void stage_two(unsigned char* dst_a, const unsigned char* src_a, uint32_t bytes_a,
+                                          unsigned char* dst_b, const unsigned char* src_b, uint32_t bytes_b,
+                                          uint64_t* bar, int use_bulk)
+{
+#ifndef SZ4_EMU
+  if (use_bulk)
+  {
+    if (threadIdx.x == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+      mbar_expect_tx(bar, bytes_a + bytes_b);
+      const uint32_t kChunk = 16384;
+      for (uint32_t o = 0; o < bytes_a; o += kChunk) bulk_g2s(dst_a + o, src_a + o, min(kChunk, bytes_a - o), bar);
+      for (uint32_t o = 0; o < bytes_b; o += kChunk) bulk_g2s(dst_b + o, src_b + o, min(kChunk, bytes_b - o), bar);
+    }
+    mbar_wait(bar, 0);
+    return;
+  }
+#endif
+  (void)bar; (void)use_bulk;
+  const uint4* sa = (const uint4*)src_a; uint4* da = (uint4*)dst_a;
+  for (uint32_t k = threadIdx.x; k < bytes_a / 16; k += blockDim.x) da[k] = sa[k];
+  const uint4* sb = (const uint4*)src_b; uint4* db = (uint4*)dst_b;
+  for (uint32_t k = threadIdx.x; k < bytes_b / 16; k += blockDim.x) db[k] = sb[k];
+  __syncthreads();
+}
+
+struct SearchView
+{
+  const unsigned char* s_data;   // staged bytes [dlo, dhi)
+  const uint16_t*      s_pe;     // staged previousExact [clo, ...)
+  const uint8_t*       g_data;   // the whole batch in HBM (for extensions that leave the staged range)
+  uint32_t dlo, dhi, clo, shift;
+
+  __device__ __forceinline__ uint32_t chain(uint32_t r) const { return s_pe[r - shift - clo]; }
+  __device__ __forceinline__ uint32_t byte_at(uint32_t pos) const
+  {
+    return pos < dhi ? s_data[pos - dlo] : g_data[pos];
+  }
+  __device__ __forceinline__ uint32_t word_at(uint32_t pos) const
+  {
+    if (pos + 4 <= dhi)
+    {
+      uint32_t a = pos - dlo;
+      const uint32_t* w = (const uint32_t*)s_data + (a >> 2);
+      return __funnelshift_r(w[0], w[1], (a & 3) * 8);
+    }
+    return ld32u(g_data + pos);
+  }
+};
+
+__global__ void __launch_bounds__(kSearchThreads, 1)
+k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, uint32_t* mlen, uint16_t* mdist,
+         uint32_t tiles_per_block, Geom g, int use_bulk)
+{
+  SZ4_DYN_SMEM(smem);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t next_pos;
+
+  const uint32_t j = blockIdx.x / tiles_per_block;
+  const uint32_t t = blockIdx.x % tiles_per_block;
+  const uint32_t t0 = block_begin(g, j) + t * kTile;
+  const uint32_t s_end = search_end(g, j);
+  if (t0 >= s_end) return;
+  const uint32_t t1 = min(t0 + kTile, s_end);
+  const uint32_t stop = block_end(g, j) - kEndLiterals;               // smallz4.h:736 end - BlockEndLiterals
+
+  SearchView v;
+  v.g_data = data;
+  v.shift = g.shift;
+  v.dlo = (t0 > kHist ? t0 - kHist : 0) & ~15u;
+  v.dhi = min(v.dlo + kDataBytes - 16, (g.n_total + 31) & ~15u);     // stays inside the zero padding
+  v.clo = (t0 > kHist + 8 ? t0 - kHist - 8 : 0) & ~7u;
+  const uint32_t chi = (t1 + 7) & ~7u;
+  unsigned char* s_data = smem;
+  uint16_t* s_pe = (uint16_t*)(smem + kDataBytes);
+  v.s_data = s_data;
+  v.s_pe = s_pe;
+
+  if (threadIdx.x == 0) next_pos = t0;
+  stage_two(s_data, data + v.dlo, v.dhi - v.dlo, (unsigned char*)s_pe, (const unsigned char*)(pe + v.clo),
+            (chi - v.clo) * 2, &bar, use_bulk);
+  __syncthreads();
+
+  const uint32_t lane = threadIdx.x & 31;
+  bool active = false, exhausted = false;
+  uint32_t p = 0, len = 1, dist = 0, total = 0, hop = 0, budget = 0;
+
+  for (;;)
+  {
+    // ---- refill idle lanes with the next positions of the tile
+    uint32_t idle = __ballot_sync(0xffffffffu, !active && !exhausted);
+    if (idle)
+    {
+      uint32_t base = 0;
+      if (lane == (uint32_t)__ffs((int)idle) - 1) base = atomicAdd(&next_pos, (uint32_t)__popc(idle));
+      base = __shfl_sync(0xffffffffu, base, __ffs((int)idle) - 1);
+      if (!active && !exhausted)
+      {
+        p = base + (uint32_t)__popc(idle & ((1u << lane) - 1));
+        if (p >= t1) exhausted = true;
+        else
+        {
+          // smallz4.h:712-717: only positions with an exact predecessor are searched
+          uint32_t own = is_twice_inserted(g, p) ? saved_pe[(p + kEndNoMatch - g.halo) / g.block_size] : s_pe[p - v.clo];
+          if (own != 0)
+          {
+            active = true; len = 1; dist = 0; total = 0; budget = g.max_chain;
+            hop = v.chain(p);                                        // smallz4.h:190 (absolute slot)
+            if (g.shift == 0) hop = own;
+          }
+        }
+      }
+    }
+    if (!__any_sync(0xffffffffu, active)) break;
+    if (!active) continue;
+
+    // ---- one candidate of this lane's chain (smallz4.h:192-252)
+    bool finish = false;
+    if (hop == 0) finish = true;
+    else
+    {
+      total += hop;
+      if (total > kWindow) finish = true;
+    }
+    if (!finish)
+    {
+      const uint32_t q = p - total;
+      hop = (total == kWindow) ? 0 : v.chain(q);                     // smallz4.h:200; at 65535 any value ends the walk
+      const uint32_t need = len + 1;                                 // atLeast - current
+      if (p + need > stop) finish = true;                            // smallz4.h:205
+      else
+      {
+        bool better = true;
+        if (len >= 4)
+        {
+          // phase 1, smallz4.h:224-233: bytes (0, need) in 4-byte groups from the top
+          if (v.byte_at(p + len) != v.byte_at(q + len)) better = false;      // top byte of the first group
+          else
+            for (int32_t off = (int32_t)need - 4; off > 0; off -= 4)
+              if (v.word_at(p + off) != v.word_at(q + off)) { better = false; break; }
+        }
+        if (better)
+        {
+          // phase 2, smallz4.h:236-243
+          uint32_t f = need;
+          while (p + f + 4 <= stop && v.word_at(p + f) == v.word_at(q + f)) f += 4;
+          while (p + f < stop && v.byte_at(p + f) == v.byte_at(q + f)) f++;
+          dist = total; len = f;
+          if (--budget == 0) finish = true;
+          else if (total == 1 && g.shift == 0 && p + len + 1 <= stop)
+          {
+            // Run of one byte: every candidate reached by hops of 1 lies in the same run and matches
+            // exactly len bytes, so the reference rejects each of them (smallz4.h:232).  Skip them.
+            while (hop == 1 && total < kWindow) { total++; hop = v.chain(p - total); }
+            if (hop == 1) hop = 0;                                   // ran into the 65535 limit
+          }
+        }
+      }
+    }
+    if (finish)
+    {
+      mlen[p] = len;
+      mdist[p] = (uint16_t)dist;
+      active = false;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Long runs (smallz4.h:632-643).  Once a position has a match {distance 1, length > 65299} the
+// reference copies {length-1, 1} to the following positions without inserting them into the
+// chains, until the length drops to 65299.  DESIGN.md "Q-run" shows that (without a dictionary)
+// the searches of all other positions are unaffected, except the first position after the skipped
+// stretch, whose predecessor becomes the seed.  Levels >= 7 fix this up in parallel here;
+// levels 1..6 do it inside the sequential greedy/lazy filter below.
+// ---------------------------------------------------------------------------------------------
+struct Seed { uint32_t pos, len; };
+
+__device__ __forceinline__ bool seed_like(const uint32_t* mlen, const uint16_t* mdist, uint32_t p)
+{
+  return mdist[p] == 1 && mlen[p] > kSameLetter;
+}
+
+__global__ void __launch_bounds__(256)
+k_seed_detect(const uint8_t* data, const uint32_t* mlen, const uint16_t* mdist, Seed* seeds, uint32_t* n_seeds,
+              uint32_t max_seeds, Geom g)
+{
+  uint32_t p = g.halo + blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= g.n_total) return;
+  if (!seed_like(mlen, mdist, p)) return;
+  const uint32_t j = (p - g.halo) / g.block_size;
+  const uint32_t b = block_begin(g, j);
+  // a true seed is the first seed-like position of its run inside its block
+  const uint8_t c = data[p];
+  for (uint32_t q = p; q > b; )
+  {
+    q--;
+    if (data[q] != c) break;
+    if (seed_like(mlen, mdist, q)) return;
+  }
+  uint32_t k = atomicAdd(n_seeds, 1u);
+  if (k < max_seeds) { seeds[k].pos = p; seeds[k].len = mlen[p]; }
+}
+
+// one CTA per seed: rewrite the skipped stretch and the position behind it
+__global__ void __launch_bounds__(256)
+k_seed_fix(uint32_t* mlen, uint16_t* mdist, const Seed* seeds, const uint32_t* n_seeds, Geom g)
+{
+  if (blockIdx.x >= *n_seeds) return;
+  const uint32_t s = seeds[blockIdx.x].pos, l = seeds[blockIdx.x].len;
+  const uint32_t count = l - kSameLetter;                       // skipped positions s+1 .. s+count
+  for (uint32_t k = 1 + threadIdx.x; k <= count; k += blockDim.x)
+  {
+    mlen[s + k] = l - k;
+    mdist[s + k] = 1;
+  }
+  if (threadIdx.x == 0)
+  {
+    const uint32_t e1 = s + count + 1;                          // first position that is inserted again
+    const uint32_t gap = e1 - s;
+    if (gap > kWindow) { mlen[e1] = 0; mdist[e1] = 0; }         // smallz4.h:668: predecessor too far
+    else if (mdist[e1] == 1) mdist[e1] = (uint16_t)gap;         // nearest candidate is the seed, not e1-1
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Levels 1..6 (smallz4.h:606-612, 727-743): greedy / lazy levels search only some positions.
+// k_search has produced the match of every eligible position; this sequential pass (one thread
+// per block) replays the reference's skipMatches / lazyEvaluation state machine and the long-run
+// shortcut, and clears the matches the reference would not have looked for.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_greedy_filter(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, uint32_t* mlen,
+                                uint16_t* mdist, Geom g)
+{
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= g.n_blocks) return;
+  const uint32_t b = block_begin(g, j), s_end = search_end(g, j);
+  uint32_t skip = 0;
+  bool peek = false;
+  uint32_t prev_len = 0, prev_dist = 0;        // matches[i-1]
+  uint32_t seed = 0;                           // last inserted position in front of a skipped stretch
+  bool prev_skipped = false;
+  for (uint32_t p = b; p < s_end; p++)
+  {
+    if (p > b && data[p] == data[p - 1] && prev_dist == 1 && prev_len > kSameLetter)
+    {
+      if (!prev_skipped) seed = p - 1;
+      prev_len -= 1;
+      mlen[p] = prev_len; mdist[p] = 1;
+      prev_skipped = true;
+      continue;
+    }
+    uint32_t own = is_twice_inserted(g, p) ? saved_pe[(p + kEndNoMatch - g.halo) / g.block_size] : pe[p];
+    uint32_t found_len = mlen[p], found_dist = mdist[p];
+    if (prev_skipped && g.shift == 0)
+    {
+      // predecessor of p in every chain is the seed (the stretch in between was never inserted)
+      uint32_t gap = p - seed;
+      if (gap > kWindow) own = 0;
+      else if (found_dist == 1) found_dist = gap;
+    }
+    prev_skipped = false;
+    prev_len = 0; prev_dist = 0;
+    if (own == 0) { mlen[p] = 0; mdist[p] = 0; continue; }
+    if (skip > 0)
+    {
+      skip--;
+      if (!peek) { mlen[p] = 0; mdist[p] = 0; continue; }
+      peek = false;
+    }
+    mlen[p] = found_len; mdist[p] = (uint16_t)found_dist;
+    prev_len = found_len; prev_dist = found_dist;
+    if (found_len != 1)
+    {
+      peek = (skip == 0);
+      skip = found_len;
+    }
+  }
+}
+
+}  // namespace sz4
