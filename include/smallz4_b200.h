@@ -52,7 +52,8 @@ const char* sz4_version(void);
 
 /* tuning / test knobs: "batch_blocks" (blocks per device batch), "block_size" (tests only: a multiple
    of 65536, >= 131072; 0 = format default), "stage_bulk" (1 = cp.async.bulk staging, 0 = plain loads),
-   "debug_keep" (keep intermediates of the last batch for sz4_debug_fetch) */
+   "debug_keep" (keep intermediates of the last batch for sz4_debug_fetch), "profile" (per-phase CUDA-event
+   timing for sz4_last_phase_ms), "force_scalar" (tests: route a dictionary stream through the scalar finder) */
 int sz4_set_option(sz4_ctx* ctx, const char* name, long long value);
 
 /* worst-case size of the frame produced for n input bytes */
@@ -84,6 +85,10 @@ size_t sz4_frame_end(unsigned char* dst, int use_legacy_format);
 
 /* milliseconds the device spent in the kernels of the last call and number of kernel launches */
 int sz4_last_stats(const sz4_ctx* ctx, double* kernel_ms, unsigned long long* launches);
+
+/* with option "profile"=1: device milliseconds of the last call per phase, out7 =
+   { sort, chain (link + exact walk), search, fix-up / greedy filter, cost DP, parse walk, emission } */
+int sz4_last_phase_ms(const sz4_ctx* ctx, double* out7);
 
 /* test hook: copy an intermediate array of the last batch to the host (needs option debug_keep=1).
    what: "pe" u16, "len_found" u32, "dist_found" u16, "len_final" u32, "cost" u32; count = elements */

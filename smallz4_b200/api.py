@@ -54,6 +54,7 @@ def load_library(path=None):
     lib.sz4_frame_end.argtypes = [vp, i32]; lib.sz4_frame_end.restype = sz
     lib.sz4_last_stats.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_ulonglong)]
     lib.sz4_last_stats.restype = i32
+    lib.sz4_last_phase_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]; lib.sz4_last_phase_ms.restype = i32
     lib.sz4_debug_fetch.argtypes = [vp, ctypes.c_char_p, vp, sz]; lib.sz4_debug_fetch.restype = i32
     return lib
 
@@ -142,6 +143,13 @@ class Compressor:
         ms, launches = ctypes.c_double(0), ctypes.c_ulonglong(0)
         self.lib.sz4_last_stats(self.h, ctypes.byref(ms), ctypes.byref(launches))
         return ms.value, launches.value
+
+    PHASES = ("sort", "chain", "search", "fixup", "dp", "path", "emit")
+
+    def last_phase_ms(self):
+        arr = (ctypes.c_double * 7)()
+        self.lib.sz4_last_phase_ms(self.h, arr)
+        return dict(zip(self.PHASES, list(arr)))
 
     def debug_fetch(self, what, count):
         dt = {"pe": np.uint16, "ph": np.uint16, "len_found": np.uint32, "dist_found": np.uint16,

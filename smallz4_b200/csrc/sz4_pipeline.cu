@@ -42,6 +42,9 @@ struct sz4_ctx
   int          device = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t  ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t  pev[8] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+  double       phase_ms[7] = { 0, 0, 0, 0, 0, 0, 0 };   // sort, chain, search, fixup, dp, path, emit
+  int          profile = 0;
   std::string  err;
   // options
   uint32_t batch_blocks = 64;
@@ -88,6 +91,7 @@ static int reserve(sz4_ctx* ctx, DevBuf& b, size_t bytes)
   b.bytes = want;
   return SZ4_OK;
 }
+#define PHASE(k) do { if (ctx->profile) CK(cudaEventRecord(ctx->pev[k], ctx->stream)); } while (0)
 #define RSV(buf, bytes) do { int r_ = reserve(ctx, ctx->buf, (bytes)); if (r_ != SZ4_OK) return r_; } while (0)
 
 static uint32_t div_up(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
@@ -146,6 +150,7 @@ static int run_batch(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
   CK(cudaMemsetAsync(ctx->pe.p, 0, ((size_t)N + 2 * kPad) * 2, ctx->stream));
   CK(cudaMemsetAsync(mlen, 0, (size_t)N * 4, ctx->stream));
   CK(cudaMemsetAsync(mdist, 0, (size_t)N * 2, ctx->stream));
+  PHASE(0);
 
   if (scalar_finder)
   {
@@ -154,6 +159,7 @@ static int run_batch(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
     RSV(scalar_state, (sizeof(uint64_t) << kHashBits) + 2 * 65536 * sizeof(uint16_t));
     CK(cudaMemsetAsync(ctx->scalar_state.p, 0xff, sizeof(uint64_t) << kHashBits, ctx->stream));
     LAUNCH(ctx, k_scalar_find, 1, 32, 0, (const uint8_t*)data, (unsigned long long*)ctx->scalar_state.p, ph, pe, mlen, mdist, g);
+    PHASE(1); PHASE(2); PHASE(3); PHASE(4);
   }
   else
   {
@@ -188,11 +194,13 @@ static int run_batch(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
         src = dst;
         dst = (dst == bufA) ? bufB : bufA;
       }
+      PHASE(1);
       LAUNCH(ctx, k_link, div_up(count, 256), 256, 0, (const uint64_t*)src, count, ph, g);
       LAUNCH(ctx, k_twice_save, div_up(g.n_blocks, 64), 64, 0, ph, saved_ph, g);
       LAUNCH(ctx, k_exact_walk, div_up(count, 256), 256, 0, (const uint8_t*)data, (const uint16_t*)ph, (const uint32_t*)saved_ph, pe, first, count, g);
       LAUNCH(ctx, k_twice_save, div_up(g.n_blocks, 64), 64, 0, pe, saved_pe, g);
 
+      PHASE(2);
       // ---- phase 2: longest match per position
       const uint32_t tiles_per_block = div_up(g.block_size, kTile);
       if (!ctx->attr_set)
@@ -202,6 +210,7 @@ static int run_batch(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
       }
       LAUNCH(ctx, k_search, g.n_blocks * tiles_per_block, kSearchThreads, kSearchSmem, (const uint8_t*)data, (const uint16_t*)pe,
              (const uint32_t*)saved_pe, mlen, mdist, tiles_per_block, g, ctx->stage_bulk);
+      PHASE(3);
       if (g.max_chain <= kLazyMax)
         LAUNCH(ctx, k_greedy_filter, div_up(g.n_blocks, 32), 32, 0, (const uint8_t*)data, (const uint16_t*)pe, (const uint32_t*)saved_pe, mlen, mdist, g);
       else
@@ -211,7 +220,9 @@ static int run_batch(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
                (Seed*)ctx->seeds.p, (uint32_t*)ctx->nseeds.p, max_seeds, g);
         LAUNCH(ctx, k_seed_fix, max_seeds, 256, 0, mlen, mdist, (const Seed*)ctx->seeds.p, (const uint32_t*)ctx->nseeds.p, g);
       }
+      PHASE(4);
     }
+    else { PHASE(1); PHASE(2); PHASE(3); PHASE(4); }
   }
 
   if (ctx->debug_keep)
@@ -230,13 +241,16 @@ static int run_batch(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
   dp.st7 = dp.st6 + N + 64;
   if (g.max_chain > kGreedyMax)                                   // smallz4.h:755
     LAUNCH(ctx, k_dp, g.n_blocks, 32, 0, mlen, (const uint16_t*)mdist, dp, g);
+  PHASE(5);
   LAUNCH(ctx, k_path, g.n_blocks, 32, 0, (const uint32_t*)mlen, (const uint16_t*)mdist, (SeqRec*)ctx->seqs.p, seq_stride,
          (uint32_t*)ctx->seq_count.p, (uint32_t*)ctx->packed.p, g);
+  PHASE(6);
   LAUNCH(ctx, k_block_offsets, 1, 32, 0, (const uint32_t*)ctx->packed.p, (BlockOut*)ctx->block_out.p,
          (unsigned long long*)ctx->seg_total.p, (uint8_t*)ctx->seg.p, g);
   const uint32_t chunks = div_up(per_block_out / 16 + 2, 256);
   LAUNCH(ctx, k_emit, g.n_blocks * chunks, 256, 0, (const uint8_t*)data, (const SeqRec*)ctx->seqs.p, seq_stride,
          (const uint32_t*)ctx->seq_count.p, (const BlockOut*)ctx->block_out.p, (uint8_t*)ctx->seg.p, chunks, g);
+  PHASE(7);
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
   CK(cudaMemcpyAsync(ctx->h_seg_total, ctx->seg_total.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
@@ -244,6 +258,13 @@ static int run_batch(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
   ctx->kernel_ms += ms;
+  if (ctx->profile)
+    for (int k = 0; k < 7; k++)
+    {
+      float pm = 0;
+      CK(cudaEventElapsedTime(&pm, ctx->pev[k], ctx->pev[k + 1]));
+      ctx->phase_ms[k] += pm;
+    }
   ctx->last_geom = g;
   return SZ4_OK;
 }
@@ -392,12 +413,18 @@ int sz4_create(sz4_ctx** out, int device)
   ctx->device = device;
   if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
+      cudaEventCreate(&ctx->pev[0]) != cudaSuccess || cudaEventCreate(&ctx->pev[1]) != cudaSuccess ||
+      cudaEventCreate(&ctx->pev[2]) != cudaSuccess || cudaEventCreate(&ctx->pev[3]) != cudaSuccess ||
+      cudaEventCreate(&ctx->pev[4]) != cudaSuccess || cudaEventCreate(&ctx->pev[5]) != cudaSuccess ||
+      cudaEventCreate(&ctx->pev[6]) != cudaSuccess || cudaEventCreate(&ctx->pev[7]) != cudaSuccess ||
       cudaMallocHost((void**)&ctx->h_seg_total, 64) != cudaSuccess)
   {
     fprintf(stderr, "smallz4_b200: cannot initialise CUDA device %d\n", device);
     delete ctx;
     return SZ4_ERR_CUDA;
   }
+  const char* env = getenv("SZ4_STAGE_BULK");          // debugging aid: 0 = stage with plain loads
+  if (env && env[0] == '0') ctx->stage_bulk = 0;
   *out = ctx;
   return SZ4_OK;
 }
@@ -413,6 +440,7 @@ void sz4_destroy(sz4_ctx* ctx)
   if (ctx->h_seg_total) cudaFreeHost(ctx->h_seg_total);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  for (int k = 0; k < 8; k++) if (ctx->pev[k]) cudaEventDestroy(ctx->pev[k]);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -426,6 +454,7 @@ int sz4_set_option(sz4_ctx* ctx, const char* name, long long value)
   if (!strcmp(name, "block_size")) { ctx->block_size_override = (uint32_t)value; return SZ4_OK; }
   if (!strcmp(name, "stage_bulk")) { ctx->stage_bulk = value != 0; return SZ4_OK; }
   if (!strcmp(name, "debug_keep")) { ctx->debug_keep = value != 0; return SZ4_OK; }
+  if (!strcmp(name, "profile")) { ctx->profile = value != 0; return SZ4_OK; }
   if (!strcmp(name, "force_scalar")) { ctx->force_scalar = value != 0; return SZ4_OK; }
   ctx->err = "unknown option";
   return SZ4_ERR_ARG;
@@ -461,6 +490,7 @@ int sz4_compress_host(sz4_ctx* ctx, const void* src, size_t n, void* dst, size_t
   if (!ctx || (!src && n) || !dst || !frame_len) return SZ4_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
   ctx->kernel_ms = 0; ctx->launches = 0;
+  for (int k = 0; k < 7; k++) ctx->phase_ms[k] = 0;
   uint8_t* out = (uint8_t*)dst;
   if (cap < 16) { ctx->err = "destination too small"; return SZ4_ERR_DST_SMALL; }
   size_t o = sz4_frame_header(out, legacy);
@@ -504,6 +534,7 @@ int sz4_compress_device(sz4_ctx* ctx, const void* d_src, size_t halo, size_t n, 
   CK(cudaSetDevice(ctx->device));
   (void)cuda_stream;   // work is ordered on the context's stream; the caller's stream is synchronised by the blocking return
   ctx->kernel_ms = 0; ctx->launches = 0;
+  for (int k = 0; k < 7; k++) ctx->phase_ms[k] = 0;
   StreamJob job;
   job.src = (const uint8_t*)d_src; job.src_on_device = true; job.halo_in_src = halo; job.n = n;
   job.first = is_first != 0; job.last = is_last != 0;
@@ -541,6 +572,13 @@ int sz4_last_stats(const sz4_ctx* ctx, double* kernel_ms, unsigned long long* la
   if (!ctx) return SZ4_ERR_ARG;
   if (kernel_ms) *kernel_ms = ctx->kernel_ms;
   if (launches) *launches = ctx->launches;
+  return SZ4_OK;
+}
+
+int sz4_last_phase_ms(const sz4_ctx* ctx, double* out7)
+{
+  if (!ctx || !out7) return SZ4_ERR_ARG;
+  for (int k = 0; k < 7; k++) out7[k] = ctx->phase_ms[k];
   return SZ4_OK;
 }
 

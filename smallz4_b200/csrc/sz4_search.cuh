@@ -23,7 +23,7 @@ enum : uint32_t
   kHist          = 65536,    // history staged in front of the tile
   kSearchThreads = 512,
   kDataBytes     = kHist + kTile + kLook + 16,
-  kChainElems    = kHist + 16 + kTile,
+  kChainElems    = kHist + 32 + kTile,
   kSearchSmem    = kDataBytes + 2 * kChainElems
 };
 
