@@ -122,6 +122,7 @@ static void find_matches(octx* c, uint64_t blk, uint64_t end, uint64_t floor_pos
         m[i].dist = 1;
         m[i].len  = prev.len - 1;
         if (c->st) c->st->selfmatch_skips++;
+        if (c->tr && c->tr->skipped) c->tr->skipped[pos] = 1;
         continue;
       }
     }

@@ -9,6 +9,7 @@
 #include "sz4_device.cuh"
 #include "sz4_sort.cuh"
 #include "sz4_chain.cuh"
+#include "sz4_runs.cuh"
 #include "sz4_search.cuh"
 #include "sz4_parse.cuh"
 #include "sz4_emit.cuh"
@@ -54,7 +55,8 @@ struct sz4_ctx
   int      force_scalar = 0;
   // device memory (grow-only)
   DevBuf data, ph, pe, mlen, mdist, scratch, hist, hist_scanned, partials, seqs, seq_count, packed,
-         saved_ph, saved_pe, seeds, nseeds, seg, block_out, seg_total, dbg_len, dbg_dist, scalar_state;
+         saved_ph, saved_pe, seeds, nseeds, seg, block_out, seg_total, dbg_len, dbg_dist, scalar_state,
+         run_fwd, ones_back, flag_last, flag_carry;
   unsigned long long* h_seg_total = nullptr;    // pinned
   // stats
   double             kernel_ms = 0;
@@ -201,6 +203,25 @@ static int run_batch(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
       LAUNCH(ctx, k_twice_save, div_up(g.n_blocks, 64), 64, 0, pe, saved_pe, g);
 
       PHASE(2);
+      // ---- helpers for runs of one byte (sz4_runs.cuh): only the undisturbed ring (no dictionary) uses them
+      RSV(run_fwd, ((size_t)N + 64) * 4);
+      RSV(ones_back, ((size_t)N + 64) * 2);
+      if (g.shift == 0)
+      {
+        const uint32_t fchunks = div_up(N, kFlagChunk);
+        RSV(flag_last, (size_t)fchunks * 4 + 64);
+        RSV(flag_carry, (size_t)fchunks * 4 + 64);
+        uint32_t* fl = (uint32_t*)ctx->flag_last.p;
+        uint32_t* fc = (uint32_t*)ctx->flag_carry.p;
+        FlagFwdRuns fr; fr.data = data; fr.n = N;
+        LAUNCH(ctx, k_flag_reduce<FlagFwdRuns>, fchunks, kFlagThreads, 0, fr, fl);
+        LAUNCH(ctx, k_flag_carry, 1, 32, 0, (const uint32_t*)fl, fc, fchunks);
+        LAUNCH(ctx, (k_flag_apply<FlagFwdRuns, uint32_t, true>), fchunks, kFlagThreads, 0, fr, (const uint32_t*)fc, (uint32_t*)ctx->run_fwd.p, 0xffffffffu);
+        FlagOnesBack fo; fo.pe = pe; fo.n = N;
+        LAUNCH(ctx, k_flag_reduce<FlagOnesBack>, fchunks, kFlagThreads, 0, fo, fl);
+        LAUNCH(ctx, k_flag_carry, 1, 32, 0, (const uint32_t*)fl, fc, fchunks);
+        LAUNCH(ctx, (k_flag_apply<FlagOnesBack, uint16_t, false>), fchunks, kFlagThreads, 0, fo, (const uint32_t*)fc, (uint16_t*)ctx->ones_back.p, 65535u);
+      }
       // ---- phase 2: longest match per position
       const uint32_t tiles_per_block = div_up(g.block_size, kTile);
       if (!ctx->attr_set)
@@ -209,7 +230,8 @@ static int run_batch(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
         ctx->attr_set = true;
       }
       LAUNCH(ctx, k_search, g.n_blocks * tiles_per_block, kSearchThreads, kSearchSmem, (const uint8_t*)data, (const uint16_t*)pe,
-             (const uint32_t*)saved_pe, mlen, mdist, tiles_per_block, g, ctx->stage_bulk);
+             (const uint32_t*)saved_pe, (const uint32_t*)ctx->run_fwd.p, (const uint16_t*)ctx->ones_back.p, mlen, mdist,
+             tiles_per_block, g, ctx->stage_bulk);
       PHASE(3);
       if (g.max_chain <= kLazyMax)
         LAUNCH(ctx, k_greedy_filter, div_up(g.n_blocks, 32), 32, 0, (const uint8_t*)data, (const uint16_t*)pe, (const uint32_t*)saved_pe, mlen, mdist, g);
@@ -435,7 +457,8 @@ void sz4_destroy(sz4_ctx* ctx)
   cudaSetDevice(ctx->device);
   DevBuf* all[] = { &ctx->data, &ctx->ph, &ctx->pe, &ctx->mlen, &ctx->mdist, &ctx->scratch, &ctx->hist, &ctx->hist_scanned,
                     &ctx->partials, &ctx->seqs, &ctx->seq_count, &ctx->packed, &ctx->saved_ph, &ctx->saved_pe, &ctx->seeds,
-                    &ctx->nseeds, &ctx->seg, &ctx->block_out, &ctx->seg_total, &ctx->dbg_len, &ctx->dbg_dist, &ctx->scalar_state };
+                    &ctx->nseeds, &ctx->seg, &ctx->block_out, &ctx->seg_total, &ctx->dbg_len, &ctx->dbg_dist, &ctx->scalar_state,
+                    &ctx->run_fwd, &ctx->ones_back, &ctx->flag_last, &ctx->flag_carry };
   for (DevBuf* b : all) if (b->p) cudaFree(b->p);
   if (ctx->h_seg_total) cudaFreeHost(ctx->h_seg_total);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);

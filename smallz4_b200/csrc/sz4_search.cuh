@@ -110,9 +110,87 @@ struct SearchView
   }
 };
 
+// One candidate of the reference loop (smallz4.h:202-247): true if it is longer than the best so far,
+// in which case len is updated.  The caller has checked that a longer match still fits (smallz4.h:205).
+__device__ __forceinline__ bool try_candidate(const SearchView& v, uint32_t p, uint32_t q, uint32_t stop, uint32_t& len)
+{
+  const uint32_t need = len + 1;
+  if (len >= 4)
+  {
+    // phase 1, smallz4.h:224-233: bytes (0, need) in 4-byte groups from the top
+    if (v.byte_at(p + len) != v.byte_at(q + len)) return false;        // top byte of the first group
+    for (int32_t off = (int32_t)need - 4; off > 0; off -= 4)
+      if (v.word_at(p + off) != v.word_at(q + off)) return false;
+  }
+  // phase 2, smallz4.h:236-243
+  uint32_t f = need;
+  while (p + f + 4 <= stop && v.word_at(p + f) == v.word_at(q + f)) f += 4;
+  while (p + f < stop && v.byte_at(p + f) == v.byte_at(q + f)) f++;
+  len = f;
+  return true;
+}
+
+// Stretch shortcut.  p lies in a run of one byte b (R = run_fwd[p] >= 4), so every member of its chain
+// starts four b's.  `top` = p - total is a candidate whose chain entry is 1: the candidates
+// q_k = top - k, k = 0..s (s = ones_back[top]) lie in ONE run of b's and have R0 + k bytes of b
+// in front of them (R0 = run_fwd[top]).  Their match lengths with p follow from the run lengths:
+//     R0+k <  R :  min(C, R0+k)            (q's run ends first)
+//     R0+k >  R :  min(C, R)               (p's run ends first)
+//     R0+k == R :  needs a real comparison (both runs end together)
+// with C = stop - p.  The reference visits them in order k = 0, 1, ... and takes every strictly
+// longer one (smallz4.h:232,246-251); that sequence is replayed here in closed form.
+// Returns true when the walk is over; otherwise total/hop are left at the last member of the stretch.
+__device__ __forceinline__ bool walk_stretch(const SearchView& v, const uint32_t* run_fwd, const uint16_t* ones_back,
+                                             uint32_t p, uint32_t stop, uint32_t R, uint32_t& total, uint32_t& hop,
+                                             uint32_t& len, uint32_t& dist, uint32_t& budget)
+{
+  const uint32_t C = stop - p;
+  const uint32_t top = p - total;
+  const uint32_t s = ones_back[top];
+  const uint32_t kmax = min(s, (uint32_t)kWindow - total);
+  const uint32_t R0 = run_fwd[top];
+  if (R0 > R)
+  {
+    // every member is deeper inside its run than p: only the first one can be an improvement
+    const uint32_t Rc = min(R, C);
+    if (Rc > len) { len = Rc; dist = total; if (--budget == 0) return true; }
+  }
+  else
+  {
+    const uint32_t kstar = R - R0;                       // the member whose run ends together with p's
+    if (kstar > 0)
+    {
+      const uint32_t kend = min(kmax, kstar - 1);
+      const uint32_t k1 = len + 1 > R0 ? len + 1 - R0 : 0;   // first member with more than len bytes
+      if (k1 <= kend)
+      {
+        if (R0 + k1 >= C) { len = C; dist = total + k1; budget--; return true; }
+        const uint32_t klast = min(kend, C - R0);        // lengths R0+k1 .. R0+klast, each one longer
+        const uint32_t cnt = klast - k1 + 1;
+        if (budget <= cnt) { const uint32_t k = k1 + budget - 1; len = R0 + k; dist = total + k; budget = 0; return true; }
+        budget -= cnt; len = R0 + klast; dist = total + klast;
+        if (len == C) return true;
+      }
+    }
+    if (kstar <= kmax)
+    {
+      if (p + len + 1 > stop) return true;
+      if (try_candidate(v, p, top - kstar, stop, len))
+      {
+        dist = total + kstar;
+        if (--budget == 0) return true;
+      }
+    }
+  }
+  if (kmax < s) return true;                             // the next hop of 1 would exceed 65535 (smallz4.h:196)
+  total += s;
+  hop = (total == kWindow) ? 0 : v.chain(p - total);
+  return p + len + 1 > stop;
+}
+
 __global__ void __launch_bounds__(kSearchThreads, 1)
-k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, uint32_t* mlen, uint16_t* mdist,
-         uint32_t tiles_per_block, Geom g, int use_bulk)
+k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, const uint32_t* run_fwd,
+         const uint16_t* ones_back, uint32_t* mlen, uint16_t* mdist, uint32_t tiles_per_block, Geom g, int use_bulk)
 {
   SZ4_DYN_SMEM(smem);
   __shared__ uint64_t bar;
@@ -146,6 +224,7 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, uint
   const uint32_t lane = threadIdx.x & 31;
   bool active = false, exhausted = false;
   uint32_t p = 0, len = 1, dist = 0, total = 0, hop = 0, budget = 0;
+  uint32_t run = 0;                    // bytes equal to data[p] from p on, when the stretch shortcut applies
 
   for (;;)
   {
@@ -168,12 +247,18 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, uint
           {
             active = true; len = 1; dist = 0; total = 0; budget = g.max_chain;
             hop = v.chain(p);                                        // smallz4.h:190 (absolute slot)
-            if (g.shift == 0) hop = own;
+            run = 0;
+            if (g.shift == 0) { hop = own; run = run_fwd[p]; }
           }
         }
       }
     }
-    if (!__any_sync(0xffffffffu, active)) break;
+    if (!__any_sync(0xffffffffu, active))
+    {
+      // nobody is walking a chain: done only when the tile has no positions left for this warp
+      if (__all_sync(0xffffffffu, exhausted)) break;
+      continue;
+    }
     if (!active) continue;
 
     // ---- one candidate of this lane's chain (smallz4.h:192-252)
@@ -192,30 +277,12 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, uint
       if (p + need > stop) finish = true;                            // smallz4.h:205
       else
       {
-        bool better = true;
-        if (len >= 4)
+        if (hop == 1 && run >= kMinMatch)
+          finish = walk_stretch(v, run_fwd, ones_back, p, stop, run, total, hop, len, dist, budget);
+        else if (try_candidate(v, p, q, stop, len))
         {
-          // phase 1, smallz4.h:224-233: bytes (0, need) in 4-byte groups from the top
-          if (v.byte_at(p + len) != v.byte_at(q + len)) better = false;      // top byte of the first group
-          else
-            for (int32_t off = (int32_t)need - 4; off > 0; off -= 4)
-              if (v.word_at(p + off) != v.word_at(q + off)) { better = false; break; }
-        }
-        if (better)
-        {
-          // phase 2, smallz4.h:236-243
-          uint32_t f = need;
-          while (p + f + 4 <= stop && v.word_at(p + f) == v.word_at(q + f)) f += 4;
-          while (p + f < stop && v.byte_at(p + f) == v.byte_at(q + f)) f++;
-          dist = total; len = f;
+          dist = total;
           if (--budget == 0) finish = true;
-          else if (total == 1 && g.shift == 0 && p + len + 1 <= stop)
-          {
-            // Run of one byte: every candidate reached by hops of 1 lies in the same run and matches
-            // exactly len bytes, so the reference rejects each of them (smallz4.h:232).  Skip them.
-            while (hop == 1 && total < kWindow) { total++; hop = v.chain(p - total); }
-            if (hop == 1) hop = 0;                                   // ran into the 65535 limit
-          }
         }
       }
     }

@@ -210,7 +210,8 @@ static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int)
 {
   memset(p, 0, sizeof(*p)); p->multiProcessorCount = 4; strcpy(p->name, "SIMT emulator"); p->major = 10; p->totalGlobalMem = (size_t)8 << 30; return 0;
 }
-static inline cudaError_t cudaMalloc(void** p, size_t n) { *p = calloc(1, n ? n : 1); return *p ? 0 : 2; }
+// device memory is NOT zeroed by the real cudaMalloc: poison it so that reads of uninitialised memory show up
+static inline cudaError_t cudaMalloc(void** p, size_t n) { *p = malloc(n ? n : 1); if (*p) memset(*p, 0xA5, n ? n : 1); return *p ? 0 : 2; }
 static inline cudaError_t cudaFree(void* p) { free(p); return 0; }
 static inline cudaError_t cudaMallocHost(void** p, size_t n) { *p = malloc(n ? n : 1); return *p ? 0 : 2; }
 static inline cudaError_t cudaHostAlloc(void** p, size_t n, unsigned) { return cudaMallocHost(p, n); }

@@ -23,7 +23,7 @@ class Stats(ctypes.Structure):
 
 class Trace(ctypes.Structure):
     _fields_ = [("prev_exact", ctypes.c_void_p), ("len_found", ctypes.c_void_p), ("dist_found", ctypes.c_void_p),
-                ("len_final", ctypes.c_void_p), ("cost", ctypes.c_void_p)]
+                ("len_final", ctypes.c_void_p), ("cost", ctypes.c_void_p), ("skipped", ctypes.c_void_p)]
 
 
 def build_oracle():
@@ -91,8 +91,8 @@ def oracle_compress(data, level=9, legacy=False, dictionary=None, block_size=0, 
         total = src.size + (65535 if d is not None else 0)
         arrays = {"prev_exact": np.zeros(total, np.uint16), "len_found": np.zeros(total, np.uint32),
                   "dist_found": np.zeros(total, np.uint16), "len_final": np.zeros(total, np.uint32),
-                  "cost": np.zeros(total, np.uint32)}
-        tr = Trace(*[arrays[k].ctypes.data for k in ("prev_exact", "len_found", "dist_found", "len_final", "cost")])
+                  "cost": np.zeros(total, np.uint32), "skipped": np.zeros(total, np.uint8)}
+        tr = Trace(*[arrays[k].ctypes.data for k in ("prev_exact", "len_found", "dist_found", "len_final", "cost", "skipped")])
     n = oracle().sz4o_compress(src.ctypes.data if src.size else None, src.size, ctypes.byref(o), dst.ctypes.data, cap,
                                ctypes.byref(st), ctypes.byref(tr) if tr is not None else None)
     assert n >= 0, "oracle compress failed"

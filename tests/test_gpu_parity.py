@@ -63,7 +63,12 @@ def test_intermediates_match_oracle(gpu):
     try:
         gpu.compress(data, level=9)
         n = len(data)
-        assert np.array_equal(gpu.debug_fetch("pe", n)[: n - 11], tr["prev_exact"][: n - 11])
+        # the parallel chain pass treats every position as inserted; positions the long-run shortcut skipped
+        # (and the one right behind such a stretch) are corrected later (DESIGN.md Q-run), so mask them here
+        sk = tr["skipped"].astype(bool)
+        keep = ~(sk | np.roll(sk, 1))
+        keep[n - 11:] = False
+        assert np.array_equal(gpu.debug_fetch("pe", n)[keep], tr["prev_exact"][keep])
         lf = gpu.debug_fetch("len_found", n); lo = tr["len_found"]
         assert np.array_equal(np.where(lf <= 1, 0, lf), np.where(lo <= 1, 0, lo))
         m = lo > 1
