@@ -14,7 +14,9 @@
 //               costs, ties resolved towards the larger index) that the warp maintains as it goes.
 //               A match of length 60 000 costs ~470 table reads instead of 60 000 additions.
 //   near phase  (32 sequential steps): candidates inside this group and the next one live in two
-//               registers per lane; one __reduce_min_sync per position picks the best of them.
+//               registers per lane; one __reduce_min_sync per position picks the best of them, issued
+//               four steps ahead of its use so that its latency is off the critical path.
+// The most recent 8192 costs and table entries stay in shared-memory rings; older ones come from L2/HBM.
 #pragma once
 #include "sz4_device.cuh"
 
@@ -36,8 +38,32 @@ __device__ __forceinline__ void take_better(uint32_t& best_cost, uint32_t& best_
   if (c < best_cost || (c == best_cost && l > best_len)) { best_cost = c; best_len = l; }
 }
 
-// minimum of cost[a..b] (a <= b, b-a < 255), ties -> largest index.  All positions two groups or more ahead.
-__device__ __forceinline__ void range_min(const DpScratch& s, uint32_t a, uint32_t b, uint32_t& out_cost, uint32_t& out_idx)
+enum : uint32_t { kDpRing = 8192, kDpSmem = 4 * kDpRing * 4 + 32 * 16 };
+
+// The warp's view of already priced positions: the most recent kDpRing of them live in shared-memory
+// rings (29-cycle reads instead of an L2 round trip), everything older is read from HBM/L2.
+struct DpView
+{
+  const uint32_t* r_cost; const uint32_t* r_st5; const uint32_t* r_st6; const uint32_t* r_st7;   // rings
+  DpScratch s;
+  uint32_t b;        // block start (batch position)
+  uint32_t ring_hi;  // block-relative positions below this are in the rings
+
+  __device__ __forceinline__ uint32_t cost(uint32_t i) const { return i < ring_hi ? r_cost[i & (kDpRing - 1)] : __ldcg(s.cost + b + i); }
+  __device__ __forceinline__ uint32_t tab(uint32_t w, uint32_t i) const
+  {
+    if (i < ring_hi)
+    {
+      const uint32_t* r = w == 128 ? r_st7 : (w == 64 ? r_st6 : r_st5);
+      return r[i & (kDpRing - 1)];
+    }
+    const uint32_t* t = w == 128 ? s.st7 : (w == 64 ? s.st6 : s.st5);
+    return __ldcg(t + b + i);
+  }
+};
+
+// minimum of cost[a..b] (block relative, a <= b, b-a < 255), ties -> largest index.
+__device__ __forceinline__ void range_min(const DpView& v, uint32_t a, uint32_t b, uint32_t& out_cost, uint32_t& out_idx)
 {
   const uint32_t span = b - a + 1;
   if (span < 32)
@@ -45,25 +71,39 @@ __device__ __forceinline__ void range_min(const DpScratch& s, uint32_t a, uint32
     uint32_t bc = 0xffffffffu, bi = a;
     for (uint32_t j = a; j <= b; j++)
     {
-      uint32_t c = __ldcg(s.cost + j);
+      uint32_t c = v.cost(j);
       if (c <= bc) { bc = c; bi = j; }
     }
     out_cost = bc; out_idx = bi;
     return;
   }
-  const uint32_t* tab = span >= 128 ? s.st7 : (span >= 64 ? s.st6 : s.st5);
   const uint32_t w = span >= 128 ? 128 : (span >= 64 ? 64 : 32);
   const uint32_t a2 = b + 1 - w;
-  const uint32_t v1 = __ldcg(tab + a), v2 = __ldcg(tab + a2);
+  const uint32_t v1 = v.tab(w, a), v2 = v.tab(w, a2);
   const uint32_t c1 = v1 >> 8, i1 = a + (255 - (v1 & 255));
   const uint32_t c2 = v2 >> 8, i2 = a2 + (255 - (v2 & 255));
   if (c2 < c1 || (c2 == c1 && i2 > i1)) { out_cost = c2; out_idx = i2; }
   else { out_cost = c1; out_idx = i1; }
 }
 
-__global__ void __launch_bounds__(32)
+// near candidates of position i0+l held in registers: this group (length lane-l, cost `cur`) and the
+// next group (length 32+lane-l, cost `prv`); packed as (cost + overhead) << 6 | (63 - length)
+__device__ __forceinline__ uint32_t near_key(uint32_t lane, int32_t l, uint32_t Ml, uint32_t cur, uint32_t prv)
+{
+  uint32_t key = 0xffffffffu;
+  const int32_t L1 = (int32_t)lane - l;
+  const uint32_t L2 = (uint32_t)(L1 + 32);
+  if (L1 >= (int32_t)kMinMatch && (uint32_t)L1 <= Ml)
+    key = ((cur + 3 + ((uint32_t)L1 >= 19 ? 1u : 0u)) << 6) | (63u - (uint32_t)L1);
+  if (L2 >= kMinMatch && L2 <= Ml)
+    key = min(key, ((prv + 3 + (L2 >= 19 ? 1u : 0u)) << 6) | (63u - L2));
+  return key;
+}
+
+__global__ void __launch_bounds__(32, 1)
 k_dp(uint32_t* mlen, const uint16_t* mdist, DpScratch s, Geom g)
 {
+  SZ4_DYN_SMEM(smem);
   const uint32_t j = blockIdx.x;
   if (j >= g.n_blocks) return;
   const uint32_t b = block_begin(g, j), n = block_len(g, j);
@@ -72,19 +112,33 @@ k_dp(uint32_t* mlen, const uint16_t* mdist, DpScratch s, Geom g)
   const uint32_t last_priced = n - (1 + kEndLiterals);           // i runs from n-6 down to 0
   const uint32_t top_group = (n - 1) / 32;
 
+  uint32_t* r_cost = (uint32_t*)smem;
+  uint32_t* r_st5 = r_cost + kDpRing;
+  uint32_t* r_st6 = r_st5 + kDpRing;
+  uint32_t* r_st7 = r_st6 + kDpRing;
+  uint4* s_tab = (uint4*)(r_st7 + kDpRing);                      // per position of the group: {M, far cost, far len | forced<<31, -}
+  DpView v;
+  v.r_cost = r_cost; v.r_st5 = r_st5; v.r_st6 = r_st6; v.r_st7 = r_st7; v.s = s; v.b = b;
+
   uint32_t run = kEndLiterals;                                   // numLiterals, uniform
+  uint32_t bump_at = 15;                                         // next run length that costs an extra byte
   uint32_t next_cost = 0;                                        // cost[i+1], uniform
   uint32_t prv = 0;                                              // cost of (group+1)*32 + lane
   uint32_t p5 = 0xffffffffu, p6a = 0xffffffffu, p6b = 0xffffffffu;   // st5 of group+1, st6 of group+1 / group+2
+
+  // matches of the first group; later groups are prefetched one group ahead
+  uint32_t Mn = 0, Dn = 0;
+  { const uint32_t i = top_group * 32 + lane; if (i < n) { Mn = mlen[b + i]; Dn = mdist[b + i]; } }
 
   for (int32_t grp = (int32_t)top_group; grp >= 0; grp--)
   {
     const uint32_t i0 = (uint32_t)grp * 32;
     const uint32_t i = i0 + lane;                                // this lane's position (block relative)
     const bool priced = i <= last_priced;
-    uint32_t M = 0, D = 0;
-    if (i < n) { M = mlen[b + i]; D = mdist[b + i]; }
-    if (!priced) M = 0;
+    uint32_t M = priced ? Mn : 0;
+    const uint32_t D = Dn;
+    if (grp > 0) { Mn = mlen[b + i - 32]; Dn = mdist[b + i - 32]; }   // i - 32 < n always
+    v.ring_hi = i0 + 32 + kDpRing;
 
     // ------------------------------ far phase: candidates ending at >= i0 + 64
     uint32_t far_cost = 0xffffffffu, far_len = 0;
@@ -92,7 +146,7 @@ k_dp(uint32_t* mlen, const uint16_t* mdist, DpScratch s, Geom g)
     if (M >= kSameLetter && D == 1)
     {
       forced = true;                                             // smallz4.h:410-416
-      far_cost = __ldcg(s.cost + b + i + M) + 1 + 2 + 1 + (M - 19) / 255;
+      far_cost = v.cost(i + M) + 1 + 2 + 1 + (M - 19) / 255;
       far_len = M;
     }
     else if (M >= kMinMatch && i + M >= i0 + 64)
@@ -105,69 +159,59 @@ k_dp(uint32_t* mlen, const uint16_t* mdist, DpScratch s, Geom g)
         uint32_t hi = e == 0 ? 18 : 18 + 255 * e;
         if (hi > M) hi = M;
         uint32_t c, at;
-        range_min(s, b + i + lo, b + i + hi, c, at);
-        take_better(far_cost, far_len, c + 3 + e, at - (b + i));
+        range_min(v, i + lo, i + hi, c, at);
+        take_better(far_cost, far_len, c + 3 + e, at - i);
         lo = hi + 1;
       }
     }
+    s_tab[lane] = make_uint4(M, far_cost, far_len | (forced ? 0x80000000u : 0u), 0);
+    __syncwarp();
 
-    // ------------------------------ near phase: 32 sequential positions, high to low
+    // ------------------------------ near phase: 32 sequential positions, high to low.  The reduction for
+    // position l only needs costs of positions >= l+4, so it is issued four steps ahead of its use.
     uint32_t cur = 0;                                            // cost of this lane's position
     uint32_t keep = 1;
+    uint32_t best[4];
+#pragma unroll
+    for (int32_t l = 31; l >= 28; l--)
+      best[l & 3] = __reduce_min_sync(0xffffffffu, near_key(lane, l, s_tab[l].x, cur, prv));
+#pragma unroll
     for (int32_t l = 31; l >= 0; l--)
     {
       const uint32_t pos = i0 + (uint32_t)l;
-      const uint32_t Ml = __shfl_sync(0xffffffffu, M, l);
-      const uint32_t fc = __shfl_sync(0xffffffffu, far_cost, l);
-      const uint32_t fl = __shfl_sync(0xffffffffu, far_len, l);
-      const uint32_t fz = __shfl_sync(0xffffffffu, (uint32_t)forced, l);
-      // candidates held in registers: this group (length lane-l) and the next one (length 32+lane-l)
-      uint32_t key = 0xffffffffu;
+      const uint4 t = s_tab[l];
+      const uint32_t bl = best[l & 3];
+      if (pos <= last_priced)                                    // uniform
       {
-        const int32_t L1 = (int32_t)lane - l;
-        const uint32_t L2 = (uint32_t)(L1 + 32);
-        if (L1 >= (int32_t)kMinMatch && (uint32_t)L1 <= Ml)
-          key = ((cur + 3 + ((uint32_t)L1 >= 19 ? 1u : 0u)) << 6) | (63u - (uint32_t)L1);
-        if (L2 >= kMinMatch && L2 <= Ml)
+        run++;
+        uint32_t lowest = next_cost + 1;
+        if (run == bump_at) { lowest++; bump_at += 255; }       // 15, 270, 525, ... (smallz4.h:398-404)
+        uint32_t choice = 1;
+        if (t.z & 0x80000000u) { lowest = t.y; choice = t.z & 0x7fffffffu; }
+        else
         {
-          uint32_t k2 = ((prv + 3 + (L2 >= 19 ? 1u : 0u)) << 6) | (63u - L2);
-          key = min(key, k2);
+          uint32_t mc = 0xffffffffu, ml = 0;
+          if (bl != 0xffffffffu) { mc = bl >> 6; ml = 63u - (bl & 63u); }
+          take_better(mc, ml, t.y, t.z);
+          if (ml != 0 && mc <= lowest) { lowest = mc; choice = ml; }
         }
+        if (choice != 1) { run = 0; bump_at = 15; }
+        next_cost = lowest;
+        if (lane == (uint32_t)l) { cur = lowest; keep = choice; }
       }
-      const uint32_t best = __reduce_min_sync(0xffffffffu, key);
-      if (pos > last_priced) continue;                           // uniform
-
-      run++;
-      uint32_t lowest = next_cost + 1;
-      if (run == 15 || (run >= 15 + 255 && (run - 15) % 255 == 0)) lowest++;
-      uint32_t choice = 1;
-      if (fz) { lowest = fc; choice = fl; }
-      else
-      {
-        uint32_t mc = 0xffffffffu, ml = 0;
-        if (best != 0xffffffffu) { mc = best >> 6; ml = 63u - (best & 63u); }
-        take_better(mc, ml, fc, fl);
-        if (ml != 0 && mc <= lowest) { lowest = mc; choice = ml; }
-      }
-      if (choice != 1) run = 0;
-      next_cost = lowest;
-      if (lane == (uint32_t)l) { cur = lowest; keep = choice; }
+      if (l >= 4)
+        best[l & 3] = __reduce_min_sync(0xffffffffu, near_key(lane, l - 4, s_tab[l - 4].x, cur, prv));
     }
 
     // ------------------------------ publish the group: costs, final lengths, sparse-table levels
-    if (i < n)
-    {
-      s.cost[b + i] = cur;
-      if (priced) mlen[b + i] = keep;
-    }
     // st5: min over cost[i .. i+31] = suffix of this group from `lane` + prefix of the next group below `lane`
     uint32_t kc = (cur << 6) | (63u - lane);                     // index lane      (this group)
     uint32_t kp = (prv << 6) | (31u - lane);                     // index 32 + lane (next group)
 #pragma unroll
     for (uint32_t d = 1; d < 32; d <<= 1)
     {
-      uint32_t t = __shfl_down_sync(0xffffffffu, kc, d);
-      if (lane + d < 32) kc = min(kc, t);
+      uint32_t tt = __shfl_down_sync(0xffffffffu, kc, d);
+      if (lane + d < 32) kc = min(kc, tt);
       uint32_t u = __shfl_up_sync(0xffffffffu, kp, d);
       if (lane >= d) kp = min(kp, u);
     }
@@ -181,7 +225,13 @@ k_dp(uint32_t* mlen, const uint16_t* mdist, DpScratch s, Geom g)
     if (p5 != 0xffffffffu && (p5 >> 8) <= (v5 >> 8)) v6 = ((p5 >> 8) << 8) | ((p5 & 255u) - 32u);
     uint32_t v7 = v6;
     if (p6b != 0xffffffffu && (p6b >> 8) <= (v6 >> 8)) v7 = ((p6b >> 8) << 8) | ((p6b & 255u) - 64u);
-    if (i < n) { s.st5[b + i] = v5; s.st6[b + i] = v6; s.st7[b + i] = v7; }
+    if (i < n)
+    {
+      s.cost[b + i] = cur; s.st5[b + i] = v5; s.st6[b + i] = v6; s.st7[b + i] = v7;
+      if (priced) mlen[b + i] = keep;
+    }
+    const uint32_t slot = i & (kDpRing - 1);
+    r_cost[slot] = cur; r_st5[slot] = v5; r_st6[slot] = v6; r_st7[slot] = v7;
     p6b = p6a; p6a = v6; p5 = v5;
     prv = cur;
     __syncwarp();
@@ -207,6 +257,18 @@ __device__ __forceinline__ uint32_t seq_bytes(uint32_t lits, uint32_t len, bool 
   return sz;
 }
 
+__device__ __forceinline__ void path_load(const uint32_t* mlen, const uint16_t* mdist, uint32_t b, uint32_t n, uint32_t sw,
+                                          uint32_t lane, uint32_t (&L)[4], uint32_t (&D)[4])
+{
+#pragma unroll
+  for (uint32_t k = 0; k < 4; k++)
+  {
+    const uint32_t i = sw + k * 32 + lane;
+    L[k] = 0; D[k] = 0;
+    if (i < n) { L[k] = mlen[b + i]; D[k] = mdist[b + i]; }
+  }
+}
+
 __global__ void __launch_bounds__(32)
 k_path(const uint32_t* mlen, const uint16_t* mdist, SeqRec* seqs, uint32_t seq_stride, uint32_t* seq_count,
        uint32_t* packed_size, Geom g)
@@ -220,17 +282,34 @@ k_path(const uint32_t* mlen, const uint16_t* mdist, SeqRec* seqs, uint32_t seq_s
   uint32_t at = 0;            // current position on the path (block relative)
   uint32_t lit_from = 0;      // start of the pending literals
   uint32_t bytes = 0, count = 0;
+  // the walk reads 128 positions at a time and keeps the following 128 in flight
+  uint32_t cur_sw = 0xffffffffu, nxt_sw = 0xffffffffu;
+  uint32_t Lc[4], Dc[4], Ln[4], Dn[4];
   while (at < n)
   {
-    const uint32_t w = at & ~31u;
-    uint32_t L = 0, Dd = 0;
-    if (w + lane < n) { L = mlen[b + w + lane]; Dd = mdist[b + w + lane]; }
-    uint32_t is_match = __ballot_sync(0xffffffffu, L > 1);
+    const uint32_t sw = at & ~127u;
+    if (sw != cur_sw)
+    {
+      if (sw == nxt_sw)
+      {
+#pragma unroll
+        for (uint32_t k = 0; k < 4; k++) { Lc[k] = Ln[k]; Dc[k] = Dn[k]; }
+      }
+      else path_load(mlen, mdist, b, n, sw, lane, Lc, Dc);
+      cur_sw = sw;
+      nxt_sw = sw + 128;
+      if (nxt_sw < n) path_load(mlen, mdist, b, n, nxt_sw, lane, Ln, Dn);
+    }
+    const uint32_t k = (at - sw) >> 5;
+    const uint32_t w = sw + k * 32;
+    const uint32_t L = k == 0 ? Lc[0] : (k == 1 ? Lc[1] : (k == 2 ? Lc[2] : Lc[3]));
+    const uint32_t Dd = k == 0 ? Dc[0] : (k == 1 ? Dc[1] : (k == 2 ? Dc[2] : Dc[3]));
+    const uint32_t is_match = __ballot_sync(0xffffffffu, L > 1);
     uint32_t o = at - w;
     while (o < 32)
     {
-      uint32_t m = is_match & ~((o == 0) ? 0u : ((1u << o) - 1u));
-      if (m == 0) { o = 32; at = w + 32; break; }
+      const uint32_t m = is_match & ~((o == 0) ? 0u : ((1u << o) - 1u));
+      if (m == 0) { at = w + 32; break; }
       const int ml = __ffs((int)m) - 1;
       const uint32_t len = __shfl_sync(0xffffffffu, L, ml);
       const uint32_t dist = __shfl_sync(0xffffffffu, Dd, ml);

@@ -62,7 +62,7 @@ struct sz4_ctx
   double             kernel_ms = 0;
   unsigned long long launches = 0;
   Geom               last_geom;
-  bool               attr_set = false;
+  bool               attr_set = false, dp_attr_set = false;
 
   int fail(const char* what, cudaError_t e)
   {
@@ -262,7 +262,14 @@ static int run_batch(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
   dp.st6 = dp.st5 + N + 64;
   dp.st7 = dp.st6 + N + 64;
   if (g.max_chain > kGreedyMax)                                   // smallz4.h:755
-    LAUNCH(ctx, k_dp, g.n_blocks, 32, 0, mlen, (const uint16_t*)mdist, dp, g);
+  {
+    if (!ctx->dp_attr_set)
+    {
+      CK(cudaFuncSetAttribute(k_dp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDpSmem));
+      ctx->dp_attr_set = true;
+    }
+    LAUNCH(ctx, k_dp, g.n_blocks, 32, kDpSmem, mlen, (const uint16_t*)mdist, dp, g);
+  }
   PHASE(5);
   LAUNCH(ctx, k_path, g.n_blocks, 32, 0, (const uint32_t*)mlen, (const uint16_t*)mdist, (SeqRec*)ctx->seqs.p, seq_stride,
          (uint32_t*)ctx->seq_count.p, (uint32_t*)ctx->packed.p, g);
