@@ -13,9 +13,12 @@
 //               range-minimum query answered from three sparse-table levels (windows of 32/64/128
 //               costs, ties resolved towards the larger index) that the warp maintains as it goes.
 //               A match of length 60 000 costs ~470 table reads instead of 60 000 additions.
-//   near phase  (32 sequential steps): candidates inside this group and the next one live in two
-//               registers per lane; one __reduce_min_sync per position picks the best of them, issued
-//               four steps ahead of its use so that its latency is off the critical path.
+//               Candidates that end in the next group up are answered from five small table levels
+//               (windows of 1..16 costs) kept in shared memory.
+//   near phase  (32 sequential steps): each lane keeps the best candidate of ITS position in two
+//               registers and updates it whenever a cost above it is decided (4 instructions, all
+//               lanes at once); the decision for position l then only needs a shuffle from lane l
+//               and the scalar recurrence cost[l] = min(cost[l+1] + literal, best candidate).
 // The most recent 8192 costs and table entries stay in shared-memory rings; older ones come from L2/HBM.
 #pragma once
 #include "sz4_device.cuh"
@@ -38,7 +41,7 @@ __device__ __forceinline__ void take_better(uint32_t& best_cost, uint32_t& best_
   if (c < best_cost || (c == best_cost && l > best_len)) { best_cost = c; best_len = l; }
 }
 
-enum : uint32_t { kDpRing = 8192, kDpSmem = 4 * kDpRing * 4 + 32 * 16 };
+enum : uint32_t { kDpRing = 8192, kDpSmem = 4 * kDpRing * 4 + 5 * 48 * 4 };
 
 // The warp's view of already priced positions: the most recent kDpRing of them live in shared-memory
 // rings (29-cycle reads instead of an L2 round trip), everything older is read from HBM/L2.
@@ -86,18 +89,17 @@ __device__ __forceinline__ void range_min(const DpView& v, uint32_t a, uint32_t 
   else { out_cost = c1; out_idx = i1; }
 }
 
-// near candidates of position i0+l held in registers: this group (length lane-l, cost `cur`) and the
-// next group (length 32+lane-l, cost `prv`); packed as (cost + overhead) << 6 | (63 - length)
-__device__ __forceinline__ uint32_t near_key(uint32_t lane, int32_t l, uint32_t Ml, uint32_t cur, uint32_t prv)
+enum : uint32_t { kDpSmall = 5 * 48 * 4 };   // five small sparse-table levels over the 32 costs of the previous group
+
+// minimum over the previous group's costs [xa..xb] (lane indices, xa <= xb), ties -> larger index.
+// lvl[k][x] = min over x..x+2^k-1 of (cost << 5 | 31 - index), padded with 0xffffffff.
+__device__ __forceinline__ void small_min(const uint32_t* lvl, uint32_t xa, uint32_t xb, uint32_t& out_cost, uint32_t& out_x)
 {
-  uint32_t key = 0xffffffffu;
-  const int32_t L1 = (int32_t)lane - l;
-  const uint32_t L2 = (uint32_t)(L1 + 32);
-  if (L1 >= (int32_t)kMinMatch && (uint32_t)L1 <= Ml)
-    key = ((cur + 3 + ((uint32_t)L1 >= 19 ? 1u : 0u)) << 6) | (63u - (uint32_t)L1);
-  if (L2 >= kMinMatch && L2 <= Ml)
-    key = min(key, ((prv + 3 + (L2 >= 19 ? 1u : 0u)) << 6) | (63u - L2));
-  return key;
+  const uint32_t span = xb - xa + 1;
+  const uint32_t k = min(4u, 31u - (uint32_t)__clz((int)span));   // span <= 32: two windows of 16 cover it
+  const uint32_t* t = lvl + k * 48;
+  const uint32_t r = min(t[xa], t[xb + 1 - (1u << k)]);
+  out_cost = r >> 5; out_x = 31u - (r & 31u);
 }
 
 __global__ void __launch_bounds__(32, 1)
@@ -116,15 +118,18 @@ k_dp(uint32_t* mlen, const uint16_t* mdist, DpScratch s, Geom g)
   uint32_t* r_st5 = r_cost + kDpRing;
   uint32_t* r_st6 = r_st5 + kDpRing;
   uint32_t* r_st7 = r_st6 + kDpRing;
-  uint4* s_tab = (uint4*)(r_st7 + kDpRing);                      // per position of the group: {M, far cost, far len | forced<<31, -}
+  uint32_t* lvl = r_st7 + kDpRing;                               // [5][48]
   DpView v;
   v.r_cost = r_cost; v.r_st5 = r_st5; v.r_st6 = r_st6; v.r_st7 = r_st7; v.s = s; v.b = b;
+  for (uint32_t k = lane; k < 5 * 48; k += 32) lvl[k] = 0xffffffffu;
+  __syncwarp();
 
   uint32_t run = kEndLiterals;                                   // numLiterals, uniform
   uint32_t bump_at = 15;                                         // next run length that costs an extra byte
   uint32_t next_cost = 0;                                        // cost[i+1], uniform
   uint32_t prv = 0;                                              // cost of (group+1)*32 + lane
   uint32_t p5 = 0xffffffffu, p6a = 0xffffffffu, p6b = 0xffffffffu;   // st5 of group+1, st6 of group+1 / group+2
+  bool have_prev = false;                                        // a group above this one exists
 
   // matches of the first group; later groups are prefetched one group ahead
   uint32_t Mn = 0, Dn = 0;
@@ -135,78 +140,114 @@ k_dp(uint32_t* mlen, const uint16_t* mdist, DpScratch s, Geom g)
     const uint32_t i0 = (uint32_t)grp * 32;
     const uint32_t i = i0 + lane;                                // this lane's position (block relative)
     const bool priced = i <= last_priced;
-    uint32_t M = priced ? Mn : 0;
+    const uint32_t M = priced ? Mn : 0;
     const uint32_t D = Dn;
     if (grp > 0) { Mn = mlen[b + i - 32]; Dn = mdist[b + i - 32]; }   // i - 32 < n always
     v.ring_hi = i0 + 32 + kDpRing;
 
-    // ------------------------------ far phase: candidates ending at >= i0 + 64
-    uint32_t far_cost = 0xffffffffu, far_len = 0;
+    // ------------------------------ parallel part (lane = position): best candidate among everything that is
+    // already priced, i.e. lengths that end in the next group or beyond.  bc/bl = its cost / length.
+    uint32_t bc = 0xffffffffu, bl = 0;
     bool forced = false;
     if (M >= kSameLetter && D == 1)
     {
       forced = true;                                             // smallz4.h:410-416
-      far_cost = v.cost(i + M) + 1 + 2 + 1 + (M - 19) / 255;
-      far_len = M;
+      bc = v.cost(i + M) + 1 + 2 + 1 + (M - 19) / 255;
+      bl = M;
     }
-    else if (M >= kMinMatch && i + M >= i0 + 64)
+    else if (M >= kMinMatch)
     {
-      uint32_t lo = i0 + 64 - i;                                 // first far length (33..64)
-      while (lo <= M)
+      if (i + M >= i0 + 64)
       {
-        // class of lo: [4,18] e=0 ; [19+255(c-1), 18+255c] e=c
-        uint32_t e = match_extra(lo);
-        uint32_t hi = e == 0 ? 18 : 18 + 255 * e;
-        if (hi > M) hi = M;
-        uint32_t c, at;
-        range_min(v, i + lo, i + hi, c, at);
-        take_better(far_cost, far_len, c + 3 + e, at - i);
-        lo = hi + 1;
+        uint32_t lo = i0 + 64 - i;                               // first length that ends two groups ahead (33..64)
+        while (lo <= M)
+        {
+          // class of lo: [4,18] e=0 ; [19+255(c-1), 18+255c] e=c
+          uint32_t e = match_extra(lo);
+          uint32_t hi = e == 0 ? 18 : 18 + 255 * e;
+          if (hi > M) hi = M;
+          uint32_t c, at;
+          range_min(v, i + lo, i + hi, c, at);
+          take_better(bc, bl, c + 3 + e, at - i);
+          lo = hi + 1;
+        }
+      }
+      if (have_prev && lane + M >= 32)
+      {
+        // lengths 32+x-lane that end at lane x of the next group: x in [max(0,lane-28), min(31,lane+M-32)]
+        const uint32_t x_hi = min(31u, lane + M - 32);
+        const uint32_t x_lo = lane >= 28 ? lane - 28 : 0;
+        if (x_lo <= x_hi)
+        {
+          uint32_t c, x;
+          const uint32_t split = lane >= 13 ? lane - 13 : 0;     // first x whose length is >= 19
+          if (split <= x_hi)
+          {
+            small_min(lvl, max(x_lo, split), x_hi, c, x);        // one extra length byte
+            take_better(bc, bl, c + 4, 32 + x - lane);
+          }
+          if (split > x_lo)
+          {
+            small_min(lvl, x_lo, min(x_hi, split - 1), c, x);
+            take_better(bc, bl, c + 3, 32 + x - lane);
+          }
+        }
       }
     }
-    s_tab[lane] = make_uint4(M, far_cost, far_len | (forced ? 0x80000000u : 0u), 0);
-    __syncwarp();
+    // lengths that end inside this group are priced on the fly below: window of valid lengths 4..M
+    const uint32_t wlen = (!forced && M >= kMinMatch) ? M - 3 : 0;
+    uint32_t bl_f = bl | (forced ? 0x80000000u : 0u);
 
-    // ------------------------------ near phase: 32 sequential positions, high to low.  The reduction for
-    // position l only needs costs of positions >= l+4, so it is issued four steps ahead of its use.
-    uint32_t cur = 0;                                            // cost of this lane's position
-    uint32_t keep = 1;
-    uint32_t best[4];
+    // ------------------------------ sequential part: 32 positions, high to low.  Every lane keeps the best
+    // candidate of its own position up to date as the costs above it become known (no reduction).
+    uint32_t cur = 0, keep = 1;
+    // lane l's candidate is final once the cost of position l+4 is known, so its broadcast is issued
+    // four steps before it is used and the shuffle latency stays off the critical path
+    uint32_t cq[4], lq[4];
 #pragma unroll
     for (int32_t l = 31; l >= 28; l--)
-      best[l & 3] = __reduce_min_sync(0xffffffffu, near_key(lane, l, s_tab[l].x, cur, prv));
+    {
+      cq[l & 3] = __shfl_sync(0xffffffffu, bc, l);
+      lq[l & 3] = __shfl_sync(0xffffffffu, bl_f, l);
+    }
 #pragma unroll
     for (int32_t l = 31; l >= 0; l--)
     {
       const uint32_t pos = i0 + (uint32_t)l;
-      const uint4 t = s_tab[l];
-      const uint32_t bl = best[l & 3];
+      const uint32_t cb = cq[l & 3];
+      const uint32_t lb = lq[l & 3];
+      uint32_t lowest = 0;                                       // the last five positions cost nothing (smallz4.h:383-389)
       if (pos <= last_priced)                                    // uniform
       {
         run++;
-        uint32_t lowest = next_cost + 1;
+        lowest = next_cost + 1;
         if (run == bump_at) { lowest++; bump_at += 255; }       // 15, 270, 525, ... (smallz4.h:398-404)
         uint32_t choice = 1;
-        if (t.z & 0x80000000u) { lowest = t.y; choice = t.z & 0x7fffffffu; }
-        else
-        {
-          uint32_t mc = 0xffffffffu, ml = 0;
-          if (bl != 0xffffffffu) { mc = bl >> 6; ml = 63u - (bl & 63u); }
-          take_better(mc, ml, t.y, t.z);
-          if (ml != 0 && mc <= lowest) { lowest = mc; choice = ml; }
-        }
+        if (lb & 0x80000000u) { lowest = cb; choice = lb & 0x7fffffffu; }
+        else if (lb != 0 && cb <= lowest) { lowest = cb; choice = lb; }
         if (choice != 1) { run = 0; bump_at = 15; }
         next_cost = lowest;
         if (lane == (uint32_t)l) { cur = lowest; keep = choice; }
       }
+      {
+        // this cost is a candidate for the positions below: length l - lane
+        const uint32_t L = (uint32_t)l - lane;
+        const uint32_t c = lowest + 3 + (L >= 19 ? 1u : 0u);
+        if (L - 4 < wlen && c < bc) { bc = c; bl_f = L; }
+      }
       if (l >= 4)
-        best[l & 3] = __reduce_min_sync(0xffffffffu, near_key(lane, l - 4, s_tab[l - 4].x, cur, prv));
+      {
+        cq[l & 3] = __shfl_sync(0xffffffffu, bc, l - 4);
+        lq[l & 3] = __shfl_sync(0xffffffffu, bl_f, l - 4);
+      }
     }
 
     // ------------------------------ publish the group: costs, final lengths, sparse-table levels
     // st5: min over cost[i .. i+31] = suffix of this group from `lane` + prefix of the next group below `lane`
     uint32_t kc = (cur << 6) | (63u - lane);                     // index lane      (this group)
     uint32_t kp = (prv << 6) | (31u - lane);                     // index 32 + lane (next group)
+    uint32_t small = (cur << 5) | (31u - lane);
+    lvl[lane] = small;
 #pragma unroll
     for (uint32_t d = 1; d < 32; d <<= 1)
     {
@@ -214,6 +255,13 @@ k_dp(uint32_t* mlen, const uint16_t* mdist, DpScratch s, Geom g)
       if (lane + d < 32) kc = min(kc, tt);
       uint32_t u = __shfl_up_sync(0xffffffffu, kp, d);
       if (lane >= d) kp = min(kp, u);
+    }
+#pragma unroll
+    for (uint32_t k = 1; k < 5; k++)
+    {
+      uint32_t tt = __shfl_down_sync(0xffffffffu, small, 1u << (k - 1));
+      if (lane + (1u << (k - 1)) < 32) small = min(small, tt);
+      lvl[k * 48 + lane] = small;
     }
     uint32_t kp_excl = __shfl_up_sync(0xffffffffu, kp, 1);
     if (lane == 0) kp_excl = 0xffffffffu;
@@ -234,6 +282,7 @@ k_dp(uint32_t* mlen, const uint16_t* mdist, DpScratch s, Geom g)
     r_cost[slot] = cur; r_st5[slot] = v5; r_st6[slot] = v6; r_st7[slot] = v7;
     p6b = p6a; p6a = v6; p5 = v5;
     prv = cur;
+    have_prev = true;
     __syncwarp();
   }
 }
