@@ -21,7 +21,7 @@ enum : uint32_t
   kTile          = 8192,     // positions per CTA
   kLook          = 3584,     // bytes staged behind the tile for match extension
   kHist          = 65536,    // history staged in front of the tile
-  kSearchThreads = 512,
+  kSearchThreads = 1024,
   kDataBytes     = kHist + kTile + kLook + 16,
   kChainElems    = kHist + 32 + kTile,
   kSearchSmem    = kDataBytes + 2 * kChainElems
@@ -112,13 +112,13 @@ struct SearchView
 
 // One candidate of the reference loop (smallz4.h:202-247): true if it is longer than the best so far,
 // in which case len is updated.  The caller has checked that a longer match still fits (smallz4.h:205).
-__device__ __forceinline__ bool try_candidate(const SearchView& v, uint32_t p, uint32_t q, uint32_t stop, uint32_t& len)
+__device__ __forceinline__ bool try_candidate(const SearchView& v, uint32_t p, uint32_t q, uint32_t stop, uint32_t& len, uint32_t& tail)
 {
   const uint32_t need = len + 1;
   if (len >= 4)
   {
     // phase 1, smallz4.h:224-233: bytes (0, need) in 4-byte groups from the top
-    if (v.byte_at(p + len) != v.byte_at(q + len)) return false;        // top byte of the first group
+    if (tail != v.byte_at(q + len)) return false;                      // top byte of the first group (tail = data[p+len])
     for (int32_t off = (int32_t)need - 4; off > 0; off -= 4)
       if (v.word_at(p + off) != v.word_at(q + off)) return false;
   }
@@ -127,6 +127,7 @@ __device__ __forceinline__ bool try_candidate(const SearchView& v, uint32_t p, u
   while (p + f + 4 <= stop && v.word_at(p + f) == v.word_at(q + f)) f += 4;
   while (p + f < stop && v.byte_at(p + f) == v.byte_at(q + f)) f++;
   len = f;
+  tail = v.byte_at(p + f);
   return true;
 }
 
@@ -142,8 +143,9 @@ __device__ __forceinline__ bool try_candidate(const SearchView& v, uint32_t p, u
 // Returns true when the walk is over; otherwise total/hop are left at the last member of the stretch.
 __device__ __forceinline__ bool walk_stretch(const SearchView& v, const uint32_t* run_fwd, const uint16_t* ones_back,
                                              uint32_t p, uint32_t stop, uint32_t R, uint32_t& total, uint32_t& hop,
-                                             uint32_t& len, uint32_t& dist, uint32_t& budget)
+                                             uint32_t& len, uint32_t& dist, uint32_t& budget, uint32_t& tail)
 {
+  const uint32_t len_in = len;
   const uint32_t C = stop - p;
   const uint32_t top = p - total;
   const uint32_t s = ones_back[top];
@@ -175,7 +177,8 @@ __device__ __forceinline__ bool walk_stretch(const SearchView& v, const uint32_t
     if (kstar <= kmax)
     {
       if (p + len + 1 > stop) return true;
-      if (try_candidate(v, p, top - kstar, stop, len))
+      if (len != len_in) tail = v.byte_at(p + len);
+      if (try_candidate(v, p, top - kstar, stop, len, tail))
       {
         dist = total + kstar;
         if (--budget == 0) return true;
@@ -183,6 +186,7 @@ __device__ __forceinline__ bool walk_stretch(const SearchView& v, const uint32_t
     }
   }
   if (kmax < s) return true;                             // the next hop of 1 would exceed 65535 (smallz4.h:196)
+  if (len != len_in) tail = v.byte_at(p + len);
   total += s;
   hop = (total == kWindow) ? 0 : v.chain(p - total);
   return p + len + 1 > stop;
@@ -225,16 +229,19 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
   bool active = false, exhausted = false;
   uint32_t p = 0, len = 1, dist = 0, total = 0, hop = 0, budget = 0;
   uint32_t run = 0;                    // bytes equal to data[p] from p on, when the stretch shortcut applies
+  uint32_t tail = 0;                   // data[p + len]: the byte a longer match has to reproduce first
 
+  // One ballot per iteration keeps `idle` (lanes that want a new position) current for all lanes.
+  uint32_t idle = 0xffffffffu;
   for (;;)
   {
     // ---- refill idle lanes with the next positions of the tile
-    uint32_t idle = __ballot_sync(0xffffffffu, !active && !exhausted);
     if (idle)
     {
       uint32_t base = 0;
-      if (lane == (uint32_t)__ffs((int)idle) - 1) base = atomicAdd(&next_pos, (uint32_t)__popc(idle));
-      base = __shfl_sync(0xffffffffu, base, __ffs((int)idle) - 1);
+      const int leader = __ffs((int)idle) - 1;
+      if (lane == (uint32_t)leader) base = atomicAdd(&next_pos, (uint32_t)__popc(idle));
+      base = __shfl_sync(0xffffffffu, base, leader);
       if (!active && !exhausted)
       {
         p = base + (uint32_t)__popc(idle & ((1u << lane) - 1));
@@ -245,53 +252,53 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
           uint32_t own = is_twice_inserted(g, p) ? saved_pe[(p + kEndNoMatch - g.halo) / g.block_size] : s_pe[p - v.clo];
           if (own != 0)
           {
-            active = true; len = 1; dist = 0; total = 0; budget = g.max_chain;
+            active = true; len = 1; dist = 0; total = 0; budget = g.max_chain; tail = 0;
             hop = v.chain(p);                                        // smallz4.h:190 (absolute slot)
             run = 0;
             if (g.shift == 0) { hop = own; run = run_fwd[p]; }
           }
         }
       }
+      if (!__any_sync(0xffffffffu, active))
+      {
+        // nobody is walking a chain: done when the tile has no positions left for this warp
+        idle = __ballot_sync(0xffffffffu, !exhausted);
+        if (idle == 0) break;
+        continue;
+      }
     }
-    if (!__any_sync(0xffffffffu, active))
-    {
-      // nobody is walking a chain: done only when the tile has no positions left for this warp
-      if (__all_sync(0xffffffffu, exhausted)) break;
-      continue;
-    }
-    if (!active) continue;
 
     // ---- one candidate of this lane's chain (smallz4.h:192-252)
-    bool finish = false;
-    if (hop == 0) finish = true;
-    else
+    if (active)
     {
-      total += hop;
-      if (total > kWindow) finish = true;
-    }
-    if (!finish)
-    {
-      const uint32_t q = p - total;
-      hop = (total == kWindow) ? 0 : v.chain(q);                     // smallz4.h:200; at 65535 any value ends the walk
-      const uint32_t need = len + 1;                                 // atLeast - current
-      if (p + need > stop) finish = true;                            // smallz4.h:205
+      bool finish = false;
+      if (hop == 0) finish = true;
       else
       {
-        if (hop == 1 && run >= kMinMatch)
-          finish = walk_stretch(v, run_fwd, ones_back, p, stop, run, total, hop, len, dist, budget);
-        else if (try_candidate(v, p, q, stop, len))
+        total += hop;
+        if (total > kWindow) finish = true;
+      }
+      if (!finish)
+      {
+        const uint32_t q = p - total;
+        hop = (total == kWindow) ? 0 : v.chain(q);                   // smallz4.h:200; at 65535 any value ends the walk
+        if (p + len + 1 > stop) finish = true;                       // smallz4.h:205 (atLeast > stop)
+        else if (hop == 1 && run >= kMinMatch)
+          finish = walk_stretch(v, run_fwd, ones_back, p, stop, run, total, hop, len, dist, budget, tail);
+        else if (try_candidate(v, p, q, stop, len, tail))
         {
           dist = total;
           if (--budget == 0) finish = true;
         }
       }
+      if (finish)
+      {
+        mlen[p] = len;
+        mdist[p] = (uint16_t)dist;
+        active = false;
+      }
     }
-    if (finish)
-    {
-      mlen[p] = len;
-      mdist[p] = (uint16_t)dist;
-      active = false;
-    }
+    idle = __ballot_sync(0xffffffffu, !active && !exhausted);
   }
 }
 
