@@ -41,7 +41,7 @@ __device__ __forceinline__ void take_better(uint32_t& best_cost, uint32_t& best_
   if (c < best_cost || (c == best_cost && l > best_len)) { best_cost = c; best_len = l; }
 }
 
-enum : uint32_t { kDpRing = 8192, kDpSmem = 4 * kDpRing * 4 + 5 * 48 * 4 };
+enum : uint32_t { kDpRing = 8192, kDpURing = 512, kDpSmem = 4 * kDpRing * 4 + 5 * 48 * 4 + kDpURing * 16 };
 
 // The warp's view of already priced positions: the most recent kDpRing of them live in shared-memory
 // rings (29-cycle reads instead of an L2 round trip), everything older is read from HBM/L2.
@@ -119,6 +119,8 @@ k_dp(uint32_t* mlen, const uint16_t* mdist, DpScratch s, Geom g)
   uint32_t* r_st6 = r_st5 + kDpRing;
   uint32_t* r_st7 = r_st6 + kDpRing;
   uint32_t* lvl = r_st7 + kDpRing;                               // [5][48]
+  uint4* u_ring = (uint4*)(lvl + 5 * 48);                        // per position: {position, match end, best of classes >= 2, its end}
+  for (uint32_t k = lane; k < kDpURing; k += 32) u_ring[k] = make_uint4(0xffffffffu, 0, 0xffffffffu, 0);
   DpView v;
   v.r_cost = r_cost; v.r_st5 = r_st5; v.r_st6 = r_st6; v.r_st7 = r_st7; v.s = s; v.b = b;
   for (uint32_t k = lane; k < 5 * 48; k += 32) lvl[k] = 0xffffffffu;
@@ -159,18 +161,52 @@ k_dp(uint32_t* mlen, const uint16_t* mdist, DpScratch s, Geom g)
     {
       if (i + M >= i0 + 64)
       {
-        uint32_t lo = i0 + 64 - i;                               // first length that ends two groups ahead (33..64)
-        while (lo <= M)
+        // Lengths that end two groups ahead or further, by class of extra length bytes:
+        //   class 1 = lengths 19..273 (3+1 bytes), class c = 19+255(c-1) .. 18+255c (3+c bytes).
+        // class 1: only its part beyond the next group
         {
-          // class of lo: [4,18] e=0 ; [19+255(c-1), 18+255c] e=c
-          uint32_t e = match_extra(lo);
-          uint32_t hi = e == 0 ? 18 : 18 + 255 * e;
-          if (hi > M) hi = M;
-          uint32_t c, at;
-          range_min(v, i + lo, i + hi, c, at);
-          take_better(bc, bl, c + 3 + e, at - i);
-          lo = hi + 1;
+          const uint32_t lo = i0 + 64 - i, hi = min(M, 273u);   // lo is 33..64
+          if (lo <= hi)
+          {
+            uint32_t c, at;
+            range_min(v, i + lo, i + hi, c, at);
+            take_better(bc, bl, c + 4, at - i);
+          }
         }
+        // classes >= 2.  The classes >= 3 of position i are the classes >= 2 of position i+255 whenever
+        // both matches end at the same position (inside one long match or run they do), each one
+        // extra byte more expensive -- so the best of "classes >= 2" is kept per position in a small
+        // ring and long matches cost two table lookups instead of one per 255 bytes of length.
+        uint32_t uc = 0xffffffffu, ul = 0;
+        if (M >= 274)
+        {
+          uint32_t c, at;
+          range_min(v, i + 274, i + min(M, 528u), c, at);
+          take_better(uc, ul, c + 5, at - i);
+          if (M >= 529)
+          {
+            const uint4 u = u_ring[(i + 255) & (kDpURing - 1)];
+            if (u.x == i + 255 && u.y == i + M)
+            {
+              if (u.z != 0xffffffffu) take_better(uc, ul, u.z + 1, u.w - i);
+            }
+            else
+            {
+              uint32_t lo = 529;
+              while (lo <= M)
+              {
+                const uint32_t e = match_extra(lo);
+                uint32_t hi = 18 + 255 * e;
+                if (hi > M) hi = M;
+                range_min(v, i + lo, i + hi, c, at);
+                take_better(uc, ul, c + 3 + e, at - i);
+                lo = hi + 1;
+              }
+            }
+          }
+          take_better(bc, bl, uc, ul);
+        }
+        u_ring[i & (kDpURing - 1)] = make_uint4(i, i + M, uc, i + ul);
       }
       if (have_prev && lane + M >= 32)
       {

@@ -1,0 +1,82 @@
+"""Kernel logic on the CPU: the product's .cu sources compiled against the SIMT emulator
+(tests/emu, test infrastructure) and compared with the oracle.  Small inputs, reduced block size
+(131072) so that several blocks, batches, lookback and the twice-inserted position are exercised;
+the GPU suite repeats the comparison at the real block size on the real kernels."""
+import pytest
+
+from emu_lib import emu_compressor
+from oracle_lib import oracle_compress
+from smallz4_b200 import corpus
+
+BS = 131072
+
+
+@pytest.fixture(scope="module")
+def emu():
+    c = emu_compressor(block_size=BS, batch_blocks=2)
+    yield c
+    c.close()
+
+
+def check(emu, data, level, legacy=False, dictionary=None):
+    got = emu.compress(data, level=level, use_legacy_format=legacy, dictionary=dictionary)
+    want, _ = oracle_compress(data, level, legacy, dictionary, block_size=BS)
+    assert got == want
+
+
+@pytest.mark.parametrize("n", [0, 1, 4, 5, 11, 12, 13, 19, 31, 32, 33, 64, 255, 1000])
+def test_edge_sizes(emu, n):
+    check(emu, corpus.make("text", n, 7).tobytes(), 9)
+    check(emu, corpus.make("text", n, 7).tobytes(), 2)
+
+
+@pytest.mark.parametrize("level", range(10))
+def test_levels_text(emu, level):
+    check(emu, corpus.make("text", 60_000, 11).tobytes(), level)
+
+
+@pytest.mark.parametrize("level", [1, 4, 7, 9])
+def test_levels_binary_and_runs(emu, level):
+    check(emu, corpus.make("binary", 50_000, 11).tobytes(), level)
+    check(emu, corpus.make("runs", 150_000, 11).tobytes(), level)
+
+
+@pytest.mark.parametrize("level", [3, 6, 9])
+def test_blocks_batches_and_tails(emu, level):
+    # 3 blocks + a short tail, two batches; tails around the 12-byte lookback rule
+    check(emu, corpus.make("mixed", 3 * BS + 777, 5).tobytes(), level)
+    for extra in (5, 12):
+        check(emu, corpus.make("text", BS + extra, 9).tobytes(), level)
+
+
+@pytest.mark.parametrize("level", [2, 5, 9])
+def test_long_runs_take_the_shortcut(emu, level):
+    """smallz4.h:632: runs above 65 299 bytes; also the position right behind a skipped stretch."""
+    check(emu, bytes(300_000), level)
+    mid = corpus.make("text", 20_000, 3).tobytes() + b"\x07" * 90_000 + corpus.make("text", 9_000, 4).tobytes()
+    check(emu, mid, level)
+
+
+def test_legacy_frames(emu):
+    check(emu, corpus.make("text", 200_000, 5).tobytes(), 9, legacy=True)
+    check(emu, corpus.make("text", 200_000, 5).tobytes(), 0, legacy=True)     # reference writes empty blocks here
+    check(emu, bytes(200_000), 5, legacy=True)
+
+
+@pytest.mark.parametrize("dict_len", [1000, 65535, 65536, 70000])
+def test_dictionary_ring_shift(emu, dict_len):
+    """Q-dict: reads of the chain ring are shifted by one slot when a dictionary is loaded."""
+    d = corpus.make("text", dict_len, 21, offset=1 << 40).tobytes()
+    data = corpus.make("text", 40_000, 21).tobytes()
+    for level in (1, 5, 9):
+        check(emu, data, level, dictionary=d)
+
+
+def test_dictionary_with_long_runs_uses_the_scalar_finder(emu):
+    check(emu, bytes(150_000), 9, dictionary=bytes(65536))
+    check(emu, bytes(150_000), 3, dictionary=bytes(30000))
+
+
+def test_periodic_data_leaves_the_cost_ring(emu):
+    """matches far longer than the DP's shared-memory ring (8192 positions) and many length classes"""
+    check(emu, (b"abcdefg" * 20000)[:120_000], 9)
