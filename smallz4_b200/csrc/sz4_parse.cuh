@@ -41,7 +41,7 @@ __device__ __forceinline__ void take_better(uint32_t& best_cost, uint32_t& best_
   if (c < best_cost || (c == best_cost && l > best_len)) { best_cost = c; best_len = l; }
 }
 
-enum : uint32_t { kDpRing = 8192, kDpURing = 512, kDpSmem = 4 * kDpRing * 4 + 5 * 48 * 4 + kDpURing * 16 };
+enum : uint32_t { kDpRing = 8192, kDpURing = 512, kDpSmem = 4 * kDpRing * 4 + 5 * 48 * 4 + kDpURing * 16 + 32 * 8 };
 
 // The warp's view of already priced positions: the most recent kDpRing of them live in shared-memory
 // rings (29-cycle reads instead of an L2 round trip), everything older is read from HBM/L2.
@@ -102,6 +102,59 @@ __device__ __forceinline__ void small_min(const uint32_t* lvl, uint32_t xa, uint
   out_cost = r >> 5; out_x = 31u - (r & 31u);
 }
 
+// The sequential part of one group: positions i0+31 .. i0, high to low (smallz4.h:389-471).
+// Every lane keeps the best candidate of ITS position in (bc, bl_f) and updates it whenever the cost
+// of a position above it is decided (no reduction).  Lane l's candidate is final once the cost of
+// position l+4 is known, so its broadcast is issued four steps before it is used.
+//   next_cost   cost[i+1]
+//   until_bump  literal decisions left until the run of literals needs another length byte:
+//               numLiterals reaches 15, 270, 525, ... (smallz4.h:398-404)
+//   out[l]      = {cost, chosen length} of position i0 + l
+template <bool kTop>
+__device__ __forceinline__ void dp_steps(uint32_t lane, uint32_t i0, uint32_t last_priced, uint32_t wlen, uint32_t bc,
+                                         uint32_t bl_f, uint32_t& next_cost, uint32_t& until_bump, uint2* out)
+{
+  uint32_t cq[4], lq[4];
+#pragma unroll
+  for (int32_t l = 31; l >= 28; l--)
+  {
+    cq[l & 3] = __shfl_sync(0xffffffffu, bc, l);
+    lq[l & 3] = __shfl_sync(0xffffffffu, bl_f, l);
+  }
+  const bool writer = lane == 0;
+#pragma unroll
+  for (int32_t l = 31; l >= 0; l--)
+  {
+    const uint32_t cb = cq[l & 3];                     // best candidate of position l: cost (all ones = none)
+    const uint32_t lb = lq[l & 3];                     // its length, bit 31 = taken unpriced (smallz4.h:410)
+    uint32_t lowest = 0, choice = 1;                   // the last five positions cost nothing (smallz4.h:383-389)
+    if (!kTop || i0 + (uint32_t)l <= last_priced)      // uniform
+    {
+      const bool bump = until_bump == 1;
+      uint32_t lit = next_cost + 1;
+      if (bump) lit++;
+      if ((int32_t)lb < 0) lit = 0xffffffffu;          // unpriced long run: the literal is not considered
+      const bool take = cb <= lit;                     // a match wins ties (smallz4.h:431)
+      lowest = min(cb, lit);
+      choice = take ? (lb & 0x7fffffffu) : 1u;
+      until_bump = take ? 15u : (bump ? 255u : until_bump - 1);
+      next_cost = lowest;
+    }
+    if (writer) out[l] = make_uint2(lowest, choice);
+    {
+      // this cost is a candidate for the positions below: length l - lane
+      const uint32_t L = (uint32_t)l - lane;
+      const uint32_t c = lowest + (L >= 19 ? 4u : 3u);
+      if (L - 4 < wlen && c < bc) { bc = c; bl_f = L; }
+    }
+    if (l >= 4)
+    {
+      cq[l & 3] = __shfl_sync(0xffffffffu, bc, l - 4);
+      lq[l & 3] = __shfl_sync(0xffffffffu, bl_f, l - 4);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(32, 1)
 k_dp(uint32_t* mlen, const uint16_t* mdist, DpScratch s, Geom g)
 {
@@ -121,13 +174,13 @@ k_dp(uint32_t* mlen, const uint16_t* mdist, DpScratch s, Geom g)
   uint32_t* lvl = r_st7 + kDpRing;                               // [5][48]
   uint4* u_ring = (uint4*)(lvl + 5 * 48);                        // per position: {position, match end, best of classes >= 2, its end}
   for (uint32_t k = lane; k < kDpURing; k += 32) u_ring[k] = make_uint4(0xffffffffu, 0, 0xffffffffu, 0);
+  uint2* s_out = (uint2*)(u_ring + kDpURing);                    // {cost, chosen length} of the group's positions
   DpView v;
   v.r_cost = r_cost; v.r_st5 = r_st5; v.r_st6 = r_st6; v.r_st7 = r_st7; v.s = s; v.b = b;
   for (uint32_t k = lane; k < 5 * 48; k += 32) lvl[k] = 0xffffffffu;
   __syncwarp();
 
-  uint32_t run = kEndLiterals;                                   // numLiterals, uniform
-  uint32_t bump_at = 15;                                         // next run length that costs an extra byte
+  uint32_t until_bump = 15 - kEndLiterals;                       // numLiterals starts at 5 (smallz4.h:387)
   uint32_t next_cost = 0;                                        // cost[i+1], uniform
   uint32_t prv = 0;                                              // cost of (group+1)*32 + lane
   uint32_t p5 = 0xffffffffu, p6a = 0xffffffffu, p6b = 0xffffffffu;   // st5 of group+1, st6 of group+1 / group+2
@@ -234,49 +287,14 @@ k_dp(uint32_t* mlen, const uint16_t* mdist, DpScratch s, Geom g)
     const uint32_t wlen = (!forced && M >= kMinMatch) ? M - 3 : 0;
     uint32_t bl_f = bl | (forced ? 0x80000000u : 0u);
 
-    // ------------------------------ sequential part: 32 positions, high to low.  Every lane keeps the best
-    // candidate of its own position up to date as the costs above it become known (no reduction).
-    uint32_t cur = 0, keep = 1;
-    // lane l's candidate is final once the cost of position l+4 is known, so its broadcast is issued
-    // four steps before it is used and the shuffle latency stays off the critical path
-    uint32_t cq[4], lq[4];
-#pragma unroll
-    for (int32_t l = 31; l >= 28; l--)
-    {
-      cq[l & 3] = __shfl_sync(0xffffffffu, bc, l);
-      lq[l & 3] = __shfl_sync(0xffffffffu, bl_f, l);
-    }
-#pragma unroll
-    for (int32_t l = 31; l >= 0; l--)
-    {
-      const uint32_t pos = i0 + (uint32_t)l;
-      const uint32_t cb = cq[l & 3];
-      const uint32_t lb = lq[l & 3];
-      uint32_t lowest = 0;                                       // the last five positions cost nothing (smallz4.h:383-389)
-      if (pos <= last_priced)                                    // uniform
-      {
-        run++;
-        lowest = next_cost + 1;
-        if (run == bump_at) { lowest++; bump_at += 255; }       // 15, 270, 525, ... (smallz4.h:398-404)
-        uint32_t choice = 1;
-        if (lb & 0x80000000u) { lowest = cb; choice = lb & 0x7fffffffu; }
-        else if (lb != 0 && cb <= lowest) { lowest = cb; choice = lb; }
-        if (choice != 1) { run = 0; bump_at = 15; }
-        next_cost = lowest;
-        if (lane == (uint32_t)l) { cur = lowest; keep = choice; }
-      }
-      {
-        // this cost is a candidate for the positions below: length l - lane
-        const uint32_t L = (uint32_t)l - lane;
-        const uint32_t c = lowest + 3 + (L >= 19 ? 1u : 0u);
-        if (L - 4 < wlen && c < bc) { bc = c; bl_f = L; }
-      }
-      if (l >= 4)
-      {
-        cq[l & 3] = __shfl_sync(0xffffffffu, bc, l - 4);
-        lq[l & 3] = __shfl_sync(0xffffffffu, bl_f, l - 4);
-      }
-    }
+    // ------------------------------ sequential part: 32 positions, high to low (dp_steps above)
+    if (i0 + 31 <= last_priced)
+      dp_steps<false>(lane, i0, last_priced, wlen, bc, bl_f, next_cost, until_bump, s_out);
+    else
+      dp_steps<true>(lane, i0, last_priced, wlen, bc, bl_f, next_cost, until_bump, s_out);
+    __syncwarp();
+    const uint2 mine = s_out[lane];
+    const uint32_t cur = mine.x, keep = mine.y;
 
     // ------------------------------ publish the group: costs, final lengths, sparse-table levels
     // st5: min over cost[i .. i+31] = suffix of this group from `lane` + prefix of the next group below `lane`

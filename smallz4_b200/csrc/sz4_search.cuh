@@ -86,32 +86,49 @@ __device__ __forceinline__ void stage_two(unsigned char* dst_a, const unsigned c
   __syncthreads();
 }
 
+// Shared-memory loads by 32-bit shared address (CUDA build) so that the hot loop does not pay for
+// generic-address arithmetic; plain pointers in the emulated build.
+#ifdef SZ4_EMU
+typedef const unsigned char* smem_addr;
+__device__ __forceinline__ smem_addr smem_base(const void* p) { return (const unsigned char*)p; }
+__device__ __forceinline__ uint32_t lds_u8(smem_addr a) { return *a; }
+__device__ __forceinline__ uint32_t lds_u16(smem_addr a) { return *(const uint16_t*)a; }
+__device__ __forceinline__ uint32_t lds_u32(smem_addr a) { return *(const uint32_t*)a; }
+#else
+typedef uint32_t smem_addr;
+__device__ __forceinline__ smem_addr smem_base(const void* p) { return smem_u32(p); }
+__device__ __forceinline__ uint32_t lds_u8(smem_addr a) { uint32_t v; asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds_u16(smem_addr a) { uint32_t v; asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds_u32(smem_addr a) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+#endif
+
 struct SearchView
 {
-  const unsigned char* s_data;   // staged bytes [dlo, dhi)
-  const uint16_t*      s_pe;     // staged previousExact [clo, ...)
-  const uint8_t*       g_data;   // the whole batch in HBM (for extensions that leave the staged range)
+  smem_addr      s_data;         // staged bytes [dlo, dhi)
+  smem_addr      s_pe;           // staged previousExact [clo, ...)
+  const uint8_t* g_data;         // the whole batch in HBM (for extensions that leave the staged range)
   uint32_t dlo, dhi, clo, shift;
 
-  __device__ __forceinline__ uint32_t chain(uint32_t r) const { return s_pe[r - shift - clo]; }
+  __device__ __forceinline__ uint32_t chain(uint32_t r) const { return lds_u16(s_pe + 2 * (r - shift - clo)); }
   __device__ __forceinline__ uint32_t byte_at(uint32_t pos) const
   {
-    return pos < dhi ? s_data[pos - dlo] : g_data[pos];
+    return pos < dhi ? lds_u8(s_data + (pos - dlo)) : g_data[pos];
   }
   __device__ __forceinline__ uint32_t word_at(uint32_t pos) const
   {
     if (pos + 4 <= dhi)
     {
-      uint32_t a = pos - dlo;
-      const uint32_t* w = (const uint32_t*)s_data + (a >> 2);
-      return __funnelshift_r(w[0], w[1], (a & 3) * 8);
+      const uint32_t a = pos - dlo;
+      const smem_addr w = s_data + (a & ~3u);
+      return __funnelshift_r(lds_u32(w), lds_u32(w + 4), (a & 3) * 8);
     }
     return ld32u(g_data + pos);
   }
 };
 
 // One candidate of the reference loop (smallz4.h:202-247): true if it is longer than the best so far,
-// in which case len is updated.  The caller has checked that a longer match still fits (smallz4.h:205).
+// in which case len and tail (= data[p + len]) are updated.  The caller has checked that a longer
+// match still fits (smallz4.h:205).
 __device__ __forceinline__ bool try_candidate(const SearchView& v, uint32_t p, uint32_t q, uint32_t stop, uint32_t& len, uint32_t& tail)
 {
   const uint32_t need = len + 1;
@@ -188,9 +205,13 @@ __device__ __forceinline__ bool walk_stretch(const SearchView& v, const uint32_t
   if (kmax < s) return true;                             // the next hop of 1 would exceed 65535 (smallz4.h:196)
   if (len != len_in) tail = v.byte_at(p + len);
   total += s;
-  hop = (total == kWindow) ? 0 : v.chain(p - total);
+  hop = v.chain(p - total);
   return p + len + 1 > stop;
 }
+
+// lane states of the walk
+enum : uint32_t { kIdle = 0, kWalk = 1, kCheck = 2, kStretch = 3, kFinish = 4 };
+enum : uint32_t { kFastHops = 4 };
 
 __global__ void __launch_bounds__(kSearchThreads, 1)
 k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, const uint32_t* run_fwd,
@@ -217,8 +238,8 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
   const uint32_t chi = (t1 + 7) & ~7u;
   unsigned char* s_data = smem;
   uint16_t* s_pe = (uint16_t*)(smem + kDataBytes);
-  v.s_data = s_data;
-  v.s_pe = s_pe;
+  v.s_data = smem_base(s_data);
+  v.s_pe = smem_base(s_pe);
 
   if (threadIdx.x == 0) next_pos = t0;
   stage_two(s_data, data + v.dlo, v.dhi - v.dlo, (unsigned char*)s_pe, (const unsigned char*)(pe + v.clo),
@@ -226,10 +247,13 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
   __syncthreads();
 
   const uint32_t lane = threadIdx.x & 31;
-  bool active = false, exhausted = false;
+  uint32_t state = kIdle;
+  bool exhausted = false;
   uint32_t p = 0, len = 1, dist = 0, total = 0, hop = 0, budget = 0;
   uint32_t run = 0;                    // bytes equal to data[p] from p on, when the stretch shortcut applies
   uint32_t tail = 0;                   // data[p + len]: the byte a longer match has to reproduce first
+  smem_addr cbase = v.s_pe, dl = v.s_data;   // &chain(p), &data[p + len] in shared memory
+  bool fast = false;                   // p + len is inside the staged bytes: candidates' bytes are too
 
   // One ballot per iteration keeps `idle` (lanes that want a new position) current for all lanes.
   uint32_t idle = 0xffffffffu;
@@ -242,24 +266,28 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
       const int leader = __ffs((int)idle) - 1;
       if (lane == (uint32_t)leader) base = atomicAdd(&next_pos, (uint32_t)__popc(idle));
       base = __shfl_sync(0xffffffffu, base, leader);
-      if (!active && !exhausted)
+      if (state == kIdle && !exhausted)
       {
         p = base + (uint32_t)__popc(idle & ((1u << lane) - 1));
         if (p >= t1) exhausted = true;
         else
         {
           // smallz4.h:712-717: only positions with an exact predecessor are searched
-          uint32_t own = is_twice_inserted(g, p) ? saved_pe[(p + kEndNoMatch - g.halo) / g.block_size] : s_pe[p - v.clo];
+          uint32_t own = is_twice_inserted(g, p) ? saved_pe[(p + kEndNoMatch - g.halo) / g.block_size]
+                                                 : lds_u16(v.s_pe + 2 * (p - v.clo));
           if (own != 0)
           {
-            active = true; len = 1; dist = 0; total = 0; budget = g.max_chain; tail = 0;
+            state = kWalk; len = 1; dist = 0; total = 0; budget = g.max_chain; tail = 0;
             hop = v.chain(p);                                        // smallz4.h:190 (absolute slot)
             run = 0;
-            if (g.shift == 0) { hop = own; run = run_fwd[p]; }
+            if (g.shift == 0) { hop = own; run = run_fwd[p]; if (run < kMinMatch) run = 0; }
+            cbase = v.s_pe + 2 * (p - v.shift - v.clo);
+            dl = v.s_data + (p + len - v.dlo);
+            fast = p + len < v.dhi;
           }
         }
       }
-      if (!__any_sync(0xffffffffu, active))
+      if (!__any_sync(0xffffffffu, state != kIdle))
       {
         // nobody is walking a chain: done when the tile has no positions left for this warp
         idle = __ballot_sync(0xffffffffu, !exhausted);
@@ -268,37 +296,60 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
       }
     }
 
-    // ---- one candidate of this lane's chain (smallz4.h:192-252)
-    if (active)
+    // ---- fast hops (smallz4.h:192-233, the rejecting path): follow the chain while the byte a longer match
+    // would need first differs.  A lane that meets anything else parks in a state for the slow part.
+#pragma unroll 1
+    for (uint32_t it = 0; it < kFastHops; it++)
     {
-      bool finish = false;
-      if (hop == 0) finish = true;
-      else
+      if (state == kWalk)
       {
-        total += hop;
-        if (total > kWindow) finish = true;
+        if (hop == 0) state = kFinish;
+        else
+        {
+          total += hop;
+          if (total > kWindow) state = kFinish;
+          else
+          {
+            // chain entry of the candidate q = p - total (at total == 65535 its value ends the walk either way)
+            hop = lds_u16(cbase - 2 * total);
+            if (run != 0 && hop == 1) state = kStretch;
+            else if (len < 4 || !fast) state = kCheck;
+            else if (lds_u8(dl - total) == tail) state = kCheck;
+          }
+        }
       }
+    }
+
+    // ---- slow part: candidates that passed the first byte, stretches, finished walks
+    if (state >= kCheck)
+    {
+      bool finish = state == kFinish;
       if (!finish)
       {
-        const uint32_t q = p - total;
-        hop = (total == kWindow) ? 0 : v.chain(q);                   // smallz4.h:200; at 65535 any value ends the walk
-        if (p + len + 1 > stop) finish = true;                       // smallz4.h:205 (atLeast > stop)
-        else if (hop == 1 && run >= kMinMatch)
+        const uint32_t len_in = len;
+        if (state == kStretch)
           finish = walk_stretch(v, run_fwd, ones_back, p, stop, run, total, hop, len, dist, budget, tail);
-        else if (try_candidate(v, p, q, stop, len, tail))
+        else if (try_candidate(v, p, p - total, stop, len, tail))
         {
           dist = total;
           if (--budget == 0) finish = true;
         }
+        if (len != len_in)
+        {
+          if (p + len + 1 > stop) finish = true;                     // smallz4.h:205: nothing longer fits
+          dl = v.s_data + (p + len - v.dlo);
+          fast = p + len < v.dhi;
+        }
+        state = kWalk;
       }
       if (finish)
       {
         mlen[p] = len;
         mdist[p] = (uint16_t)dist;
-        active = false;
+        state = kIdle;
       }
     }
-    idle = __ballot_sync(0xffffffffu, !active && !exhausted);
+    idle = __ballot_sync(0xffffffffu, state == kIdle && !exhausted);
   }
 }
 
