@@ -127,7 +127,8 @@ struct SearchView
 };
 
 // One candidate of the reference loop (smallz4.h:202-247): true if it is longer than the best so far,
-// in which case len and tail (= data[p + len]) are updated.  The caller has checked that a longer
+// in which case len and tail are updated.  tail = the four bytes p+len-3 .. p+len, i.e. the first group
+// the reference's backward scan compares (smallz4.h:224-225).  The caller has checked that a longer
 // match still fits (smallz4.h:205).
 __device__ __forceinline__ bool try_candidate(const SearchView& v, uint32_t p, uint32_t q, uint32_t stop, uint32_t& len, uint32_t& tail)
 {
@@ -135,8 +136,8 @@ __device__ __forceinline__ bool try_candidate(const SearchView& v, uint32_t p, u
   if (len >= 4)
   {
     // phase 1, smallz4.h:224-233: bytes (0, need) in 4-byte groups from the top
-    if (tail != v.byte_at(q + len)) return false;                      // top byte of the first group (tail = data[p+len])
-    for (int32_t off = (int32_t)need - 4; off > 0; off -= 4)
+    if (tail != v.word_at(q + len - 3)) return false;                  // first group from the top
+    for (int32_t off = (int32_t)need - 8; off > 0; off -= 4)
       if (v.word_at(p + off) != v.word_at(q + off)) return false;
   }
   // phase 2, smallz4.h:236-243
@@ -144,7 +145,7 @@ __device__ __forceinline__ bool try_candidate(const SearchView& v, uint32_t p, u
   while (p + f + 4 <= stop && v.word_at(p + f) == v.word_at(q + f)) f += 4;
   while (p + f < stop && v.byte_at(p + f) == v.byte_at(q + f)) f++;
   len = f;
-  tail = v.byte_at(p + f);
+  tail = v.word_at(p + f - 3);
   return true;
 }
 
@@ -194,7 +195,7 @@ __device__ __forceinline__ bool walk_stretch(const SearchView& v, const uint32_t
     if (kstar <= kmax)
     {
       if (p + len + 1 > stop) return true;
-      if (len != len_in) tail = v.byte_at(p + len);
+      if (len != len_in) tail = v.word_at(p + len - 3);
       if (try_candidate(v, p, top - kstar, stop, len, tail))
       {
         dist = total + kstar;
@@ -203,7 +204,7 @@ __device__ __forceinline__ bool walk_stretch(const SearchView& v, const uint32_t
     }
   }
   if (kmax < s) return true;                             // the next hop of 1 would exceed 65535 (smallz4.h:196)
-  if (len != len_in) tail = v.byte_at(p + len);
+  if (len != len_in) tail = v.word_at(p + len - 3);
   total += s;
   hop = v.chain(p - total);
   return p + len + 1 > stop;
@@ -211,7 +212,7 @@ __device__ __forceinline__ bool walk_stretch(const SearchView& v, const uint32_t
 
 // lane states of the walk
 enum : uint32_t { kIdle = 0, kWalk = 1, kCheck = 2, kStretch = 3, kFinish = 4 };
-enum : uint32_t { kFastHops = 4 };
+enum : uint32_t { kFastHops = 8 };
 
 __global__ void __launch_bounds__(kSearchThreads, 1)
 k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, const uint32_t* run_fwd,
@@ -251,8 +252,8 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
   bool exhausted = false;
   uint32_t p = 0, len = 1, dist = 0, total = 0, hop = 0, budget = 0;
   uint32_t run = 0;                    // bytes equal to data[p] from p on, when the stretch shortcut applies
-  uint32_t tail = 0;                   // data[p + len]: the byte a longer match has to reproduce first
-  smem_addr cbase = v.s_pe, dl = v.s_data;   // &chain(p), &data[p + len] in shared memory
+  uint32_t tail = 0;                   // bytes p+len-3 .. p+len: the group a longer match has to reproduce first
+  smem_addr cbase = v.s_pe, dl = v.s_data;   // &chain(p), &data[p + len - 3] in shared memory
   bool fast = false;                   // p + len is inside the staged bytes: candidates' bytes are too
 
   // One ballot per iteration keeps `idle` (lanes that want a new position) current for all lanes.
@@ -283,7 +284,7 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
             if (g.shift == 0) { hop = own; run = run_fwd[p]; if (run < kMinMatch) run = 0; }
             cbase = v.s_pe + 2 * (p - v.shift - v.clo);
             dl = v.s_data + (p + len - v.dlo);
-            fast = p + len < v.dhi;
+            fast = false;                                            // the first candidate is taken unseen
           }
         }
       }
@@ -313,8 +314,15 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
             // chain entry of the candidate q = p - total (at total == 65535 its value ends the walk either way)
             hop = lds_u16(cbase - 2 * total);
             if (run != 0 && hop == 1) state = kStretch;
-            else if (len < 4 || !fast) state = kCheck;
-            else if (lds_u8(dl - total) == tail) state = kCheck;
+            else if (!fast) state = kCheck;
+            else
+            {
+              // the candidate's bytes q+len-3 .. q+len (unaligned 32-bit read from shared memory)
+              const smem_addr a = dl - total;
+              const uint32_t sh = (uint32_t)(a - v.s_data) & 3u;
+              const smem_addr w = a - sh;
+              if (__funnelshift_r(lds_u32(w), lds_u32(w + 4), sh * 8) == tail) state = kCheck;
+            }
           }
         }
       }
@@ -337,8 +345,8 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
         if (len != len_in)
         {
           if (p + len + 1 > stop) finish = true;                     // smallz4.h:205: nothing longer fits
-          dl = v.s_data + (p + len - v.dlo);
-          fast = p + len < v.dhi;
+          dl = v.s_data + (p + len - 3 - v.dlo);
+          fast = len >= 4 && p + len + 1 <= v.dhi;
         }
         state = kWalk;
       }
