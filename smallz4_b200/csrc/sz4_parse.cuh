@@ -22,6 +22,7 @@
 // The most recent 8192 costs and table entries stay in shared-memory rings; older ones come from L2/HBM.
 #pragma once
 #include "sz4_device.cuh"
+#include "sz4_sort.cuh"
 
 namespace sz4
 {
@@ -373,8 +374,7 @@ __device__ __forceinline__ void path_load(const uint32_t* mlen, const uint16_t* 
 }
 
 __global__ void __launch_bounds__(32)
-k_path(const uint32_t* mlen, const uint16_t* mdist, SeqRec* seqs, uint32_t seq_stride, uint32_t* seq_count,
-       uint32_t* packed_size, Geom g)
+k_path(const uint32_t* mlen, const uint16_t* mdist, SeqRec* seqs, uint32_t seq_stride, uint32_t* seq_count, Geom g)
 {
   const uint32_t j = blockIdx.x;
   if (j >= g.n_blocks) return;
@@ -383,9 +383,9 @@ k_path(const uint32_t* mlen, const uint16_t* mdist, SeqRec* seqs, uint32_t seq_s
   SeqRec* out = seqs + (size_t)j * seq_stride;
 
   uint32_t at = 0;            // current position on the path (block relative)
-  uint32_t lit_from = 0;      // start of the pending literals
-  uint32_t bytes = 0, count = 0;
-  // the walk reads 128 positions at a time and keeps the following 128 in flight
+  uint32_t count = 0;
+  // the walk reads 128 positions at a time and keeps the following 128 in flight; it only lists the
+  // matches on the path -- sizes and output offsets are computed in parallel afterwards (k_seq_scan)
   uint32_t cur_sw = 0xffffffffu, nxt_sw = 0xffffffffu;
   uint32_t Lc[4], Dc[4], Ln[4], Dn[4];
   while (at < n)
@@ -411,25 +411,58 @@ k_path(const uint32_t* mlen, const uint16_t* mdist, SeqRec* seqs, uint32_t seq_s
     uint32_t o = at - w;
     while (o < 32)
     {
-      const uint32_t m = is_match & ~((o == 0) ? 0u : ((1u << o) - 1u));
+      const uint32_t m = is_match & (0xffffffffu << o);
       if (m == 0) { at = w + 32; break; }
       const int ml = __ffs((int)m) - 1;
       const uint32_t len = __shfl_sync(0xffffffffu, L, ml);
       const uint32_t dist = __shfl_sync(0xffffffffu, Dd, ml);
       const uint32_t pos = w + (uint32_t)ml;
-      if (lane == 0) { SeqRec r; r.pos = pos; r.len = len; r.dist = dist; r.out = bytes; out[count] = r; }
-      bytes += seq_bytes(pos - lit_from, len, false);
+      if (lane == 0) { SeqRec r; r.pos = pos; r.len = len; r.dist = dist; r.out = 0; out[count] = r; }
       count++;
       at = pos + len;
-      lit_from = at;
       o = at - w;                      // may be >= 32: leaves the window
     }
   }
   // final literals (smallz4.h:292-308: the last token has no match)
-  if (lane == 0) { SeqRec r; r.pos = n; r.len = 0; r.dist = 0; r.out = bytes; out[count] = r; }
-  bytes += seq_bytes(n - lit_from, 0, true);
+  if (lane == 0) { SeqRec r; r.pos = n; r.len = 0; r.dist = 0; r.out = 0; out[count] = r; }
   count++;
-  if (lane == 0) { seq_count[j] = count; packed_size[j] = bytes; }
+  if (lane == 0) seq_count[j] = count;
+}
+
+// Offsets of the sequences inside the compressed block = exclusive prefix sum of their sizes
+// (smallz4.h:303-367 gives the size of one sequence).  One CTA per block.
+__global__ void __launch_bounds__(1024)
+k_seq_scan(SeqRec* seqs, uint32_t seq_stride, const uint32_t* seq_count, uint32_t* packed_size, Geom g)
+{
+  __shared__ uint32_t ws[32];
+  __shared__ uint32_t tot;
+  const uint32_t j = blockIdx.x;
+  if (j >= g.n_blocks) return;
+  SeqRec* sq = seqs + (size_t)j * seq_stride;
+  const uint32_t cnt = seq_count[j];
+  uint32_t carry = 0;
+  for (uint32_t base = 0; base < cnt; base += 4 * blockDim.x)
+  {
+    const uint32_t k0 = base + threadIdx.x * 4;
+    uint32_t sz[4] = { 0, 0, 0, 0 };
+    uint32_t prev_end = 0;
+    if (k0 > 0 && k0 < cnt) { const SeqRec q = sq[k0 - 1]; prev_end = q.pos + q.len; }
+#pragma unroll
+    for (uint32_t t = 0; t < 4; t++)
+      if (k0 + t < cnt)
+      {
+        const SeqRec r = sq[k0 + t];
+        sz[t] = seq_bytes(r.pos - prev_end, r.len, r.len == 0);
+        prev_end = r.pos + r.len;
+      }
+    uint32_t run = carry + block_excl_scan(sz[0] + sz[1] + sz[2] + sz[3], ws, &tot);
+#pragma unroll
+    for (uint32_t t = 0; t < 4; t++)
+      if (k0 + t < cnt) { sq[k0 + t].out = run; run += sz[t]; }
+    carry += tot;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) packed_size[j] = carry;
 }
 
 }  // namespace sz4

@@ -272,7 +272,9 @@ static int run_batch(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
   }
   PHASE(5);
   LAUNCH(ctx, k_path, g.n_blocks, 32, 0, (const uint32_t*)mlen, (const uint16_t*)mdist, (SeqRec*)ctx->seqs.p, seq_stride,
-         (uint32_t*)ctx->seq_count.p, (uint32_t*)ctx->packed.p, g);
+         (uint32_t*)ctx->seq_count.p, g);
+  LAUNCH(ctx, k_seq_scan, g.n_blocks, 1024, 0, (SeqRec*)ctx->seqs.p, seq_stride, (const uint32_t*)ctx->seq_count.p,
+         (uint32_t*)ctx->packed.p, g);
   PHASE(6);
   LAUNCH(ctx, k_block_offsets, 1, 32, 0, (const uint32_t*)ctx->packed.p, (BlockOut*)ctx->block_out.p,
          (unsigned long long*)ctx->seg_total.p, (uint8_t*)ctx->seg.p, g);
