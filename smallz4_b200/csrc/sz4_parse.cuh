@@ -384,24 +384,38 @@ k_path(const uint32_t* mlen, const uint16_t* mdist, SeqRec* seqs, uint32_t seq_s
 
   uint32_t at = 0;            // current position on the path (block relative)
   uint32_t count = 0;
-  // the walk reads 128 positions at a time and keeps the following 128 in flight; it only lists the
-  // matches on the path -- sizes and output offsets are computed in parallel afterwards (k_seq_scan)
-  uint32_t cur_sw = 0xffffffffu, nxt_sw = 0xffffffffu;
-  uint32_t Lc[4], Dc[4], Ln[4], Dn[4];
+  // the walk reads 128 positions at a time and keeps the following 256 in flight (two sets of registers,
+  // enough to cover a DRAM round trip); it only lists the matches on the path -- sizes and output
+  // offsets are computed in parallel afterwards (k_seq_scan)
+  uint32_t cur_sw = 0xffffffffu, n1_sw = 0xffffffffu, n2_sw = 0xffffffffu;
+  uint32_t Lc[4], Dc[4], L1[4], D1[4], L2[4], D2[4];
   while (at < n)
   {
     const uint32_t sw = at & ~127u;
     if (sw != cur_sw)
     {
-      if (sw == nxt_sw)
+      if (sw == n1_sw)
       {
 #pragma unroll
-        for (uint32_t k = 0; k < 4; k++) { Lc[k] = Ln[k]; Dc[k] = Dn[k]; }
+        for (uint32_t k = 0; k < 4; k++) { Lc[k] = L1[k]; Dc[k] = D1[k]; L1[k] = L2[k]; D1[k] = D2[k]; }
+        n1_sw = n2_sw;
       }
-      else path_load(mlen, mdist, b, n, sw, lane, Lc, Dc);
+      else if (sw == n2_sw)
+      {
+#pragma unroll
+        for (uint32_t k = 0; k < 4; k++) { Lc[k] = L2[k]; Dc[k] = D2[k]; }
+        n1_sw = sw + 128;
+        if (n1_sw < n) path_load(mlen, mdist, b, n, n1_sw, lane, L1, D1);
+      }
+      else
+      {
+        path_load(mlen, mdist, b, n, sw, lane, Lc, Dc);
+        n1_sw = sw + 128;
+        if (n1_sw < n) path_load(mlen, mdist, b, n, n1_sw, lane, L1, D1);
+      }
       cur_sw = sw;
-      nxt_sw = sw + 128;
-      if (nxt_sw < n) path_load(mlen, mdist, b, n, nxt_sw, lane, Ln, Dn);
+      n2_sw = sw + 256;
+      if (n2_sw < n) path_load(mlen, mdist, b, n, n2_sw, lane, L2, D2);
     }
     const uint32_t k = (at - sw) >> 5;
     const uint32_t w = sw + k * 32;

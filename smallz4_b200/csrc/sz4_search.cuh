@@ -242,7 +242,7 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
   v.s_data = smem_base(s_data);
   v.s_pe = smem_base(s_pe);
 
-  if (threadIdx.x == 0) next_pos = t0;
+  if (threadIdx.x == 0) next_pos = 0;
   stage_two(s_data, data + v.dlo, v.dhi - v.dlo, (unsigned char*)s_pe, (const unsigned char*)(pe + v.clo),
             (chi - v.clo) * 2, &bar, use_bulk);
   __syncthreads();
@@ -269,14 +269,20 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
       base = __shfl_sync(0xffffffffu, base, leader);
       if (state == kIdle && !exhausted)
       {
-        p = base + (uint32_t)__popc(idle & ((1u << lane) - 1));
-        if (p >= t1) exhausted = true;
+        // The tile is handed out in three passes, longest expected chains first: a near previous
+        // occurrence means a frequent 4-gram, i.e. a long chain (about 65536 / distance members).
+        const uint32_t vidx = base + (uint32_t)__popc(idle & ((1u << lane) - 1));
+        const uint32_t span = t1 - t0;
+        if (vidx >= 3 * span) exhausted = true;
         else
         {
+          const uint32_t pass = vidx >= 2 * span ? 2 : (vidx >= span ? 1 : 0);
+          p = t0 + vidx - pass * span;
           // smallz4.h:712-717: only positions with an exact predecessor are searched
           uint32_t own = is_twice_inserted(g, p) ? saved_pe[(p + kEndNoMatch - g.halo) / g.block_size]
                                                  : lds_u16(v.s_pe + 2 * (p - v.clo));
-          if (own != 0)
+          const uint32_t cls = own < 48 ? 0 : (own < 1024 ? 1 : 2);
+          if (own != 0 && cls == pass)
           {
             state = kWalk; len = 1; dist = 0; total = 0; budget = g.max_chain; tail = 0;
             hop = v.chain(p);                                        // smallz4.h:190 (absolute slot)
