@@ -212,7 +212,7 @@ __device__ __forceinline__ bool walk_stretch(const SearchView& v, const uint32_t
 
 // lane states of the walk
 enum : uint32_t { kIdle = 0, kWalk = 1, kCheck = 2, kStretch = 3, kFinish = 4 };
-enum : uint32_t { kFastHops = 8 };
+enum : uint32_t { kFastHops = 8, kStretchMin = 8 };
 
 __global__ void __launch_bounds__(kSearchThreads, 1)
 k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, const uint32_t* run_fwd,
@@ -255,6 +255,7 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
   uint32_t tail = 0;                   // bytes p+len-3 .. p+len: the group a longer match has to reproduce first
   smem_addr cbase = v.s_pe, dl = v.s_data;   // &chain(p), &data[p + len - 3] in shared memory
   bool fast = false;                   // p + len is inside the staged bytes: candidates' bytes are too
+  uint32_t ones = 0;                   // consecutive chain entries equal to 1 seen so far
 
   // One ballot per iteration keeps `idle` (lanes that want a new position) current for all lanes.
   uint32_t idle = 0xffffffffu;
@@ -284,7 +285,7 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
           const uint32_t cls = own < 48 ? 0 : (own < 1024 ? 1 : 2);
           if (own != 0 && cls == pass)
           {
-            state = kWalk; len = 1; dist = 0; total = 0; budget = g.max_chain; tail = 0;
+            state = kWalk; len = 1; dist = 0; total = 0; budget = g.max_chain; tail = 0; ones = 0;
             hop = v.chain(p);                                        // smallz4.h:190 (absolute slot)
             run = 0;
             if (g.shift == 0) { hop = own; run = run_fwd[p]; if (run < kMinMatch) run = 0; }
@@ -319,15 +320,21 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
           {
             // chain entry of the candidate q = p - total (at total == 65535 its value ends the walk either way)
             hop = lds_u16(cbase - 2 * total);
-            if (run != 0 && hop == 1) state = kStretch;
+            // a long series of 1-hops is a run of one byte: after kStretchMin of them the rest of the
+            // stretch is done in closed form (walk_stretch); short ones are cheaper to walk
+            ones = (hop == 1) ? ones + 1 : 0;
+            if (run != 0 && ones >= kStretchMin) state = kStretch;
             else if (!fast) state = kCheck;
             else
             {
-              // the candidate's bytes q+len-3 .. q+len (unaligned 32-bit read from shared memory)
+              // the candidate's bytes q+len-3 .. q+len against p's: top byte first, then the whole group
               const smem_addr a = dl - total;
-              const uint32_t sh = (uint32_t)(a - v.s_data) & 3u;
-              const smem_addr w = a - sh;
-              if (__funnelshift_r(lds_u32(w), lds_u32(w + 4), sh * 8) == tail) state = kCheck;
+              if (lds_u8(a + 3) == (tail >> 24))
+              {
+                const uint32_t sh = (uint32_t)(a - v.s_data) & 3u;
+                const smem_addr w = a - sh;
+                if (__funnelshift_r(lds_u32(w), lds_u32(w + 4), sh * 8) == tail) state = kCheck;
+              }
             }
           }
         }
@@ -342,7 +349,10 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
       {
         const uint32_t len_in = len;
         if (state == kStretch)
+        {
           finish = walk_stretch(v, run_fwd, ones_back, p, stop, run, total, hop, len, dist, budget, tail);
+          ones = 0;
+        }
         else if (try_candidate(v, p, p - total, stop, len, tail))
         {
           dist = total;
