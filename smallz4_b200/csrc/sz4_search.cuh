@@ -320,10 +320,10 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
           {
             // chain entry of the candidate q = p - total (at total == 65535 its value ends the walk either way)
             hop = lds_u16(cbase - 2 * total);
-            // a long series of 1-hops is a run of one byte: after kStretchMin of them the rest of the
-            // stretch is done in closed form (walk_stretch); short ones are cheaper to walk
+            // a series of 1-hops is a run of one byte: the stretch is done in closed form (walk_stretch),
+            // except that short stretches are cheaper to walk while the in-smem filter applies
             ones = (hop == 1) ? ones + 1 : 0;
-            if (run != 0 && ones >= kStretchMin) state = kStretch;
+            if (run != 0 && ones >= (fast ? (uint32_t)kStretchMin : 1u)) state = kStretch;
             else if (!fast) state = kCheck;
             else
             {
