@@ -69,20 +69,22 @@ def run_reference(args, rank, world):
     shard = args.ref_shard_kb * 1024
     kind = reference_kind()
     total_mb = args.size_mb
-    # shards are spread over the whole workload so that every corpus component is sampled
-    stride = max(shard, (total_mb * MB // cores) // shard * shard)
-    jobs = [(i * stride, shard, 9, kind) for i in range(cores)]
+    # many small shards spread evenly over the whole workload (every corpus component is sampled in
+    # proportion) and handed out dynamically, so that no core idles behind a slow shard
+    pieces = cores * args.ref_shards_per_core
+    stride = max(shard, (total_mb * MB // pieces) // shard * shard)
+    jobs = [(i * stride, shard, 9, kind) for i in range(pieces)]
     ctx = mp.get_context("fork")
     with ctx.Pool(cores) as pool:
         for _ in range(args.warmup):
-            pool.map(_ref_worker, jobs)
+            pool.map(_ref_worker, jobs, chunksize=1)
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            pool.map(_ref_worker, jobs)
+            pool.map(_ref_worker, jobs, chunksize=1)
         dt = time.perf_counter() - t0
-    bytes_per_step = cores * shard
+    bytes_per_step = pieces * shard
     gbs = bytes_per_step * args.steps / dt / 1e9
-    sample = f"{cores} shards of {args.ref_shard_kb} KiB spread over the workload, one process per core, per step"
+    sample = f"{pieces} shards of {args.ref_shard_kb} KiB spread evenly over the workload, {cores} processes (one per core), per step"
     line = {
         "impl": "reference", "metric": METRIC, "value": gbs, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -144,7 +146,7 @@ def cpu_baseline(size_mb, sample_kb):
     from oracle_lib import oracle_compress, reference, reference_compress
     from smallz4_b200 import corpus
     kind = reference_kind()
-    pieces = 4
+    pieces = 32           # many small pieces: the corpus components differ by 100x in reference speed
     piece = sample_kb * 1024 // pieces
     stride = (size_mb * MB // pieces) // piece * piece
     t = 0.0
@@ -157,7 +159,7 @@ def cpu_baseline(size_mb, sample_kb):
             oracle_compress(data, 9)
         t += time.perf_counter() - t0
     return {"value": pieces * piece / t / 1e9, "unit": "GB/s", "cores": 1, "kind": kind,
-            "sample": f"{pieces} pieces of {piece // 1024} KiB spread over the workload ({t:.1f} s of CPU)"}
+            "sample": f"{pieces} pieces of {piece // 1024} KiB spread evenly over the workload ({t:.1f} s of CPU)"}
 
 
 def run_ours(args, rank, world, local_rank):
@@ -270,8 +272,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size-mb", type=int, default=256)
     ap.add_argument("--batch-blocks", type=int, default=64)
-    ap.add_argument("--cpu-sample-kb", type=int, default=1024)
-    ap.add_argument("--ref-shard-kb", type=int, default=256)
+    ap.add_argument("--cpu-sample-kb", type=int, default=4096)
+    ap.add_argument("--ref-shard-kb", type=int, default=64)
+    ap.add_argument("--ref-shards-per-core", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -120,3 +120,30 @@ def test_lz4_callback_api(gpu):
     gpu.lz4(get, out.append, max_chain_length=65535)
     want, _ = oracle_compress(data, 9)
     assert b"".join(out) == want
+
+
+def test_cli_matches_reference_flags(tmp_path):
+    """The drop-in CLI (same flags as smallz4.cpp:166-326) through files and pipes: -9 default, -l, -D, -f."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cli = os.path.join(root, "smallz4_b200", "smallz4")
+    if not os.path.exists(cli):
+        import sys
+        sys.path.insert(0, root)
+        import __graft_entry__
+        __graft_entry__.build()
+    data = corpus.make("text", 400_000, seed=17).tobytes()
+    src = tmp_path / "in.bin"
+    src.write_bytes(data)
+    out = tmp_path / "out.lz4"
+    subprocess.run([cli, str(src), str(out)], check=True)
+    assert out.read_bytes() == oracle_compress(data, 9)[0]
+    subprocess.run([cli, "-f4", str(src), str(out)], check=True)                      # -f and a level in one flag group
+    assert out.read_bytes() == oracle_compress(data, 4)[0]
+    r = subprocess.run([cli, "-l", "-7"], input=data, capture_output=True, check=True)  # stdin -> stdout, legacy frame
+    assert r.stdout == oracle_compress(data, 7, legacy=True)[0]
+    d = corpus.make("text", 65536, seed=17, offset=1 << 40).tobytes()
+    (tmp_path / "dict.bin").write_bytes(d)
+    subprocess.run([cli, "-f", "-D", str(tmp_path / "dict.bin"), str(src), str(out)], check=True)
+    assert out.read_bytes() == oracle_compress(data, 9, dictionary=d)[0]
+    assert subprocess.run([cli, str(src), str(out)], capture_output=True).returncode != 0   # exists, no -f
