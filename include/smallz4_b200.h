@@ -90,6 +90,9 @@ int sz4_last_stats(const sz4_ctx* ctx, double* kernel_ms, unsigned long long* la
    { sort, chain (link + exact walk), search, fix-up / greedy filter, cost DP, parse walk, emission } */
 int sz4_last_phase_ms(const sz4_ctx* ctx, double* out7);
 
+/* segments of the cost DP that failed verification in the last call and were priced again */
+long long sz4_last_dp_redos(const sz4_ctx* ctx);
+
 /* test hook: copy an intermediate array of the last batch to the host (needs option debug_keep=1).
    what: "pe" u16, "len_found" u32, "dist_found" u16, "len_final" u32, "cost" u32; count = elements */
 int sz4_debug_fetch(sz4_ctx* ctx, const char* what, void* dst, size_t count);

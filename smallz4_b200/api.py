@@ -55,6 +55,7 @@ def load_library(path=None):
     lib.sz4_last_stats.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_ulonglong)]
     lib.sz4_last_stats.restype = i32
     lib.sz4_last_phase_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]; lib.sz4_last_phase_ms.restype = i32
+    lib.sz4_last_dp_redos.argtypes = [vp]; lib.sz4_last_dp_redos.restype = ctypes.c_longlong
     lib.sz4_debug_fetch.argtypes = [vp, ctypes.c_char_p, vp, sz]; lib.sz4_debug_fetch.restype = i32
     return lib
 
@@ -150,6 +151,9 @@ class Compressor:
         arr = (ctypes.c_double * 7)()
         self.lib.sz4_last_phase_ms(self.h, arr)
         return dict(zip(self.PHASES, list(arr)))
+
+    def last_dp_redos(self):
+        return self.lib.sz4_last_dp_redos(self.h)
 
     def debug_fetch(self, what, count):
         dt = {"pe": np.uint16, "ph": np.uint16, "len_found": np.uint32, "dist_found": np.uint16,

@@ -42,24 +42,66 @@ __device__ __forceinline__ void take_better(uint32_t& best_cost, uint32_t& best_
   if (c < best_cost || (c == best_cost && l > best_len)) { best_cost = c; best_len = l; }
 }
 
-enum : uint32_t { kDpRing = 8192, kDpURing = 512, kDpSmem = 4 * kDpRing * 4 + 5 * 48 * 4 + kDpURing * 16 + 32 * 8 };
+// Tunables of the segment-parallel DP (overridable for the emulated tests, which use small blocks)
+#ifndef SZ4_DP_RING
+#define SZ4_DP_RING 2048
+#endif
+#ifndef SZ4_DP_SEG
+#define SZ4_DP_SEG 32768
+#endif
+#ifndef SZ4_DP_WARM
+#define SZ4_DP_WARM 2048
+#endif
+#ifndef SZ4_DP_SLACK
+#define SZ4_DP_SLACK 512
+#endif
+enum : uint32_t
+{
+  kDpRing  = SZ4_DP_RING,    // positions whose costs / tables stay in shared memory
+  kDpSeg   = SZ4_DP_SEG,     // nominal segment length
+  kDpWarm  = SZ4_DP_WARM,    // positions a segment starts to the right of its own range
+  kDpSlack = SZ4_DP_SLACK,   // a boundary is only placed where no match from the left reaches further than this
+  kDpOvl   = kDpWarm + 64,   // entries of a segment's warm-up overlay
+  kDpURing = 512,
+  kDpSmem  = 4 * kDpRing * 4 + 5 * 48 * 4 + kDpURing * 16 + 32 * 8
+};
+
+// One segment of a block: own range [lo, hi) (block relative, multiples of 32; hi == block length for the
+// top segment).  reach = largest i + len[i] over i < hi: positions left of hi never look beyond it.
+struct DpTask { uint32_t lo, hi, reach, pad_; };
+// until_bump after the positions >= hi / >= lo were done; cum = offset of this segment's costs to the true ones
+struct DpState { uint32_t ub_hi, ub_lo, redone, cum; };
+struct DpOverlay { uint32_t* cost; uint32_t* st5; uint32_t* st6; uint32_t* st7; };   // warm-up results, kDpOvl each
 
 // The warp's view of already priced positions: the most recent kDpRing of them live in shared-memory
-// rings (29-cycle reads instead of an L2 round trip), everything older is read from HBM/L2.
+// rings (29-cycle reads instead of an L2 round trip), everything older is read from HBM/L2 -- from the
+// segment's private overlay for positions at or beyond `split` (its warm-up zone), else from the block arrays.
 struct DpView
 {
   const uint32_t* r_cost; const uint32_t* r_st5; const uint32_t* r_st6; const uint32_t* r_st7;   // rings
   DpScratch s;
+  DpOverlay o;       // o.cost == nullptr: no overlay (everything is in the block arrays)
   uint32_t b;        // block start (batch position)
   uint32_t ring_hi;  // block-relative positions below this are in the rings
+  uint32_t split;
 
-  __device__ __forceinline__ uint32_t cost(uint32_t i) const { return i < ring_hi ? r_cost[i & (kDpRing - 1)] : __ldcg(s.cost + b + i); }
+  __device__ __forceinline__ uint32_t cost(uint32_t i) const
+  {
+    if (i < ring_hi) return r_cost[i & (kDpRing - 1)];
+    if (o.cost != nullptr && i >= split) return __ldcg(o.cost + (i - split));
+    return __ldcg(s.cost + b + i);
+  }
   __device__ __forceinline__ uint32_t tab(uint32_t w, uint32_t i) const
   {
     if (i < ring_hi)
     {
       const uint32_t* r = w == 128 ? r_st7 : (w == 64 ? r_st6 : r_st5);
       return r[i & (kDpRing - 1)];
+    }
+    if (o.cost != nullptr && i >= split)
+    {
+      const uint32_t* t = w == 128 ? o.st7 : (w == 64 ? o.st6 : o.st5);
+      return __ldcg(t + (i - split));
     }
     const uint32_t* t = w == 128 ? s.st7 : (w == 64 ? s.st6 : s.st5);
     return __ldcg(t + b + i);
@@ -156,17 +198,23 @@ __device__ __forceinline__ void dp_steps(uint32_t lane, uint32_t i0, uint32_t la
   }
 }
 
-__global__ void __launch_bounds__(32, 1)
-k_dp(uint32_t* mlen, const uint16_t* mdist, DpScratch s, Geom g)
+// The DP over the positions [lo, start) of one block, high to low, where start = hi (resume: the state at
+// hi is loaded from the block arrays, which hold the true values of the segment to the right) or
+// start = min(hi + kDpWarm, n) (cold start: as if the block ended at `start`; the results for positions
+// >= hi go to the overlay and only serve to let the costs settle before the own range begins).
+// Own-range results go to the block arrays (s) and the final lengths to mfin.
+__device__ __forceinline__ void dp_segment(const uint32_t* mlen, const uint16_t* mdist, uint32_t* mfin, DpScratch s, DpOverlay ovl,
+                                           uint32_t b, uint32_t n, uint32_t lo, uint32_t hi, bool resume, uint32_t ub_resume,
+                                           unsigned char* smem, uint32_t& ub_hi, uint32_t& ub_lo)
 {
-  SZ4_DYN_SMEM(smem);
-  const uint32_t j = blockIdx.x;
-  if (j >= g.n_blocks) return;
-  const uint32_t b = block_begin(g, j), n = block_len(g, j);
-  if (n <= kEndNoMatch) return;                                  // smallz4.h:755
   const uint32_t lane = threadIdx.x;
-  const uint32_t last_priced = n - (1 + kEndLiterals);           // i runs from n-6 down to 0
-  const uint32_t top_group = (n - 1) / 32;
+  const uint32_t start = resume ? hi : min(hi + (uint32_t)kDpWarm, n);
+  const bool true_end = (start == n) && !resume;
+  // a cold start prices the positions as if the block ended at `start` (smallz4.h:389: the last five are free,
+  // matches end five bytes before the end); at the real end this is the reference's own rule
+  const uint32_t last_priced = resume ? 0xffffffffu : start - (1 + kEndLiterals);
+  const uint32_t cap_end = (resume || true_end) ? 0xffffffffu : start - kEndLiterals;
+  const uint32_t top_group = (start - 1) / 32;
 
   uint32_t* r_cost = (uint32_t*)smem;
   uint32_t* r_st5 = r_cost + kDpRing;
@@ -178,6 +226,8 @@ k_dp(uint32_t* mlen, const uint16_t* mdist, DpScratch s, Geom g)
   uint2* s_out = (uint2*)(u_ring + kDpURing);                    // {cost, chosen length} of the group's positions
   DpView v;
   v.r_cost = r_cost; v.r_st5 = r_st5; v.r_st6 = r_st6; v.r_st7 = r_st7; v.s = s; v.b = b;
+  v.o = ovl; v.split = hi;
+  if (resume) v.o.cost = nullptr;
   for (uint32_t k = lane; k < 5 * 48; k += 32) lvl[k] = 0xffffffffu;
   __syncwarp();
 
@@ -186,116 +236,161 @@ k_dp(uint32_t* mlen, const uint16_t* mdist, DpScratch s, Geom g)
   uint32_t prv = 0;                                              // cost of (group+1)*32 + lane
   uint32_t p5 = 0xffffffffu, p6a = 0xffffffffu, p6b = 0xffffffffu;   // st5 of group+1, st6 of group+1 / group+2
   bool have_prev = false;                                        // a group above this one exists
+  ub_hi = until_bump;
+  if (resume)
+  {
+    // take over the state at position hi from the block arrays
+    until_bump = ub_resume;
+    const uint32_t i = hi + lane;
+    prv = i < n ? __ldcg(s.cost + b + i) : 0;
+    next_cost = __shfl_sync(0xffffffffu, prv, 0);
+    if (i < n) { p5 = __ldcg(s.st5 + b + i); p6a = __ldcg(s.st6 + b + i); }
+    if (i + 32 < n) p6b = __ldcg(s.st6 + b + i + 32);
+    have_prev = true;
+    uint32_t small = (prv << 5) | (31u - lane);
+    lvl[lane] = small;
+#pragma unroll
+    for (uint32_t k = 1; k < 5; k++)
+    {
+      uint32_t tt = __shfl_down_sync(0xffffffffu, small, 1u << (k - 1));
+      if (lane + (1u << (k - 1)) < 32) small = min(small, tt);
+      lvl[k * 48 + lane] = small;
+    }
+    for (uint32_t y = hi + lane; y < hi + kDpRing && y < n; y += 32)
+    {
+      const uint32_t slot = y & (kDpRing - 1);
+      r_cost[slot] = __ldcg(s.cost + b + y); r_st5[slot] = __ldcg(s.st5 + b + y);
+      r_st6[slot] = __ldcg(s.st6 + b + y);  r_st7[slot] = __ldcg(s.st7 + b + y);
+    }
+    __syncwarp();
+  }
 
   // matches of the first group; later groups are prefetched one group ahead
   uint32_t Mn = 0, Dn = 0;
-  { const uint32_t i = top_group * 32 + lane; if (i < n) { Mn = mlen[b + i]; Dn = mdist[b + i]; } }
+  { const uint32_t i = top_group * 32 + lane; if (i < start) { Mn = mlen[b + i]; Dn = mdist[b + i]; } }
 
-  for (int32_t grp = (int32_t)top_group; grp >= 0; grp--)
+  for (int32_t grp = (int32_t)top_group; grp >= (int32_t)(lo / 32); grp--)
   {
     const uint32_t i0 = (uint32_t)grp * 32;
     const uint32_t i = i0 + lane;                                // this lane's position (block relative)
-    const bool priced = i <= last_priced;
-    const uint32_t M = priced ? Mn : 0;
+    const bool exists = i < start;
+    const bool priced = exists && i <= last_priced;
+    uint32_t M = priced ? Mn : 0;
+    if (M != 0 && i + M > cap_end) { M = cap_end > i ? cap_end - i : 0; if (M < kMinMatch) M = 0; }
     const uint32_t D = Dn;
-    if (grp > 0) { Mn = mlen[b + i - 32]; Dn = mdist[b + i - 32]; }   // i - 32 < n always
-    v.ring_hi = i0 + 32 + kDpRing;
+    if (grp > 0) { Mn = mlen[b + i - 32]; Dn = mdist[b + i - 32]; }   // i - 32 < start always
+    v.ring_hi = min(i0 + 32 + (uint32_t)kDpRing, resume ? 0xffffffffu : start);
 
-    // ------------------------------ parallel part (lane = position): best candidate among everything that is
-    // already priced, i.e. lengths that end in the next group or beyond.  bc/bl = its cost / length.
-    uint32_t bc = 0xffffffffu, bl = 0;
-    bool forced = false;
-    if (M >= kSameLetter && D == 1)
+    uint32_t cur, keep;
+    if (i0 + 31 <= last_priced && __all_sync(0xffffffffu, M == 0))
     {
-      forced = true;                                             // smallz4.h:410-416
-      bc = v.cost(i + M) + 1 + 2 + 1 + (M - 19) / 255;
-      bl = M;
+      // no position of the group has a match: 32 literal steps in closed form.  The next length byte is
+      // due at step until_bump (smallz4.h:398-404), at most once within 32 steps.
+      const uint32_t t = 32 - lane;                              // steps from the top of the group down to this lane
+      cur = next_cost + t + (t >= until_bump ? 1u : 0u);
+      keep = 1;
+      next_cost += 32 + (until_bump <= 32 ? 1u : 0u);
+      until_bump = until_bump <= 32 ? 255 - (32 - until_bump) : until_bump - 32;
     }
-    else if (M >= kMinMatch)
+    else
     {
-      if (i + M >= i0 + 64)
+      // ------------------------------ parallel part (lane = position): best candidate among everything that is
+      // already priced, i.e. lengths that end in the next group or beyond.  bc/bl = its cost / length.
+      uint32_t bc = 0xffffffffu, bl = 0;
+      bool forced = false;
+      if (M >= kSameLetter && D == 1)
       {
-        // Lengths that end two groups ahead or further, by class of extra length bytes:
-        //   class 1 = lengths 19..273 (3+1 bytes), class c = 19+255(c-1) .. 18+255c (3+c bytes).
-        // class 1: only its part beyond the next group
+        forced = true;                                             // smallz4.h:410-416
+        bc = v.cost(i + M) + 1 + 2 + 1 + (M - 19) / 255;
+        bl = M;
+      }
+      else if (M >= kMinMatch)
+      {
+        if (i + M >= i0 + 64)
         {
-          const uint32_t lo = i0 + 64 - i, hi = min(M, 273u);   // lo is 33..64
-          if (lo <= hi)
+          // Lengths that end two groups ahead or further, by class of extra length bytes:
+          //   class 1 = lengths 19..273 (3+1 bytes), class c = 19+255(c-1) .. 18+255c (3+c bytes).
+          // class 1: only its part beyond the next group
+          {
+            const uint32_t lo = i0 + 64 - i, hi = min(M, 273u);   // lo is 33..64
+            if (lo <= hi)
+            {
+              uint32_t c, at;
+              range_min(v, i + lo, i + hi, c, at);
+              take_better(bc, bl, c + 4, at - i);
+            }
+          }
+          // classes >= 2.  The classes >= 3 of position i are the classes >= 2 of position i+255 whenever
+          // both matches end at the same position (inside one long match or run they do), each one
+          // extra byte more expensive -- so the best of "classes >= 2" is kept per position in a small
+          // ring and long matches cost two table lookups instead of one per 255 bytes of length.
+          uint32_t uc = 0xffffffffu, ul = 0;
+          if (M >= 274)
           {
             uint32_t c, at;
-            range_min(v, i + lo, i + hi, c, at);
-            take_better(bc, bl, c + 4, at - i);
-          }
-        }
-        // classes >= 2.  The classes >= 3 of position i are the classes >= 2 of position i+255 whenever
-        // both matches end at the same position (inside one long match or run they do), each one
-        // extra byte more expensive -- so the best of "classes >= 2" is kept per position in a small
-        // ring and long matches cost two table lookups instead of one per 255 bytes of length.
-        uint32_t uc = 0xffffffffu, ul = 0;
-        if (M >= 274)
-        {
-          uint32_t c, at;
-          range_min(v, i + 274, i + min(M, 528u), c, at);
-          take_better(uc, ul, c + 5, at - i);
-          if (M >= 529)
-          {
-            const uint4 u = u_ring[(i + 255) & (kDpURing - 1)];
-            if (u.x == i + 255 && u.y == i + M)
+            range_min(v, i + 274, i + min(M, 528u), c, at);
+            take_better(uc, ul, c + 5, at - i);
+            if (M >= 529)
             {
-              if (u.z != 0xffffffffu) take_better(uc, ul, u.z + 1, u.w - i);
-            }
-            else
-            {
-              uint32_t lo = 529;
-              while (lo <= M)
+              const uint4 u = u_ring[(i + 255) & (kDpURing - 1)];
+              if (u.x == i + 255 && u.y == i + M)
               {
-                const uint32_t e = match_extra(lo);
-                uint32_t hi = 18 + 255 * e;
-                if (hi > M) hi = M;
-                range_min(v, i + lo, i + hi, c, at);
-                take_better(uc, ul, c + 3 + e, at - i);
-                lo = hi + 1;
+                if (u.z != 0xffffffffu) take_better(uc, ul, u.z + 1, u.w - i);
+              }
+              else
+              {
+                uint32_t lo = 529;
+                while (lo <= M)
+                {
+                  const uint32_t e = match_extra(lo);
+                  uint32_t hi = 18 + 255 * e;
+                  if (hi > M) hi = M;
+                  range_min(v, i + lo, i + hi, c, at);
+                  take_better(uc, ul, c + 3 + e, at - i);
+                  lo = hi + 1;
+                }
               }
             }
+            take_better(bc, bl, uc, ul);
           }
-          take_better(bc, bl, uc, ul);
+          u_ring[i & (kDpURing - 1)] = make_uint4(i, i + M, uc, i + ul);
         }
-        u_ring[i & (kDpURing - 1)] = make_uint4(i, i + M, uc, i + ul);
-      }
-      if (have_prev && lane + M >= 32)
-      {
-        // lengths 32+x-lane that end at lane x of the next group: x in [max(0,lane-28), min(31,lane+M-32)]
-        const uint32_t x_hi = min(31u, lane + M - 32);
-        const uint32_t x_lo = lane >= 28 ? lane - 28 : 0;
-        if (x_lo <= x_hi)
+        if (have_prev && lane + M >= 32)
         {
-          uint32_t c, x;
-          const uint32_t split = lane >= 13 ? lane - 13 : 0;     // first x whose length is >= 19
-          if (split <= x_hi)
+          // lengths 32+x-lane that end at lane x of the next group: x in [max(0,lane-28), min(31,lane+M-32)]
+          const uint32_t x_hi = min(31u, lane + M - 32);
+          const uint32_t x_lo = lane >= 28 ? lane - 28 : 0;
+          if (x_lo <= x_hi)
           {
-            small_min(lvl, max(x_lo, split), x_hi, c, x);        // one extra length byte
-            take_better(bc, bl, c + 4, 32 + x - lane);
-          }
-          if (split > x_lo)
-          {
-            small_min(lvl, x_lo, min(x_hi, split - 1), c, x);
-            take_better(bc, bl, c + 3, 32 + x - lane);
+            uint32_t c, x;
+            const uint32_t split = lane >= 13 ? lane - 13 : 0;     // first x whose length is >= 19
+            if (split <= x_hi)
+            {
+              small_min(lvl, max(x_lo, split), x_hi, c, x);        // one extra length byte
+              take_better(bc, bl, c + 4, 32 + x - lane);
+            }
+            if (split > x_lo)
+            {
+              small_min(lvl, x_lo, min(x_hi, split - 1), c, x);
+              take_better(bc, bl, c + 3, 32 + x - lane);
+            }
           }
         }
       }
-    }
-    // lengths that end inside this group are priced on the fly below: window of valid lengths 4..M
-    const uint32_t wlen = (!forced && M >= kMinMatch) ? M - 3 : 0;
-    uint32_t bl_f = bl | (forced ? 0x80000000u : 0u);
+      // lengths that end inside this group are priced on the fly below: window of valid lengths 4..M
+      const uint32_t wlen = (!forced && M >= kMinMatch) ? M - 3 : 0;
+      uint32_t bl_f = bl | (forced ? 0x80000000u : 0u);
 
-    // ------------------------------ sequential part: 32 positions, high to low (dp_steps above)
-    if (i0 + 31 <= last_priced)
-      dp_steps<false>(lane, i0, last_priced, wlen, bc, bl_f, next_cost, until_bump, s_out);
-    else
-      dp_steps<true>(lane, i0, last_priced, wlen, bc, bl_f, next_cost, until_bump, s_out);
-    __syncwarp();
-    const uint2 mine = s_out[lane];
-    const uint32_t cur = mine.x, keep = mine.y;
+      // ------------------------------ sequential part: 32 positions, high to low (dp_steps above)
+      if (i0 + 31 <= last_priced)
+        dp_steps<false>(lane, i0, last_priced, wlen, bc, bl_f, next_cost, until_bump, s_out);
+      else
+        dp_steps<true>(lane, i0, last_priced, wlen, bc, bl_f, next_cost, until_bump, s_out);
+      __syncwarp();
+      const uint2 mine = s_out[lane];
+      cur = mine.x; keep = mine.y;
+
+    }
 
     // ------------------------------ publish the group: costs, final lengths, sparse-table levels
     // st5: min over cost[i .. i+31] = suffix of this group from `lane` + prefix of the next group below `lane`
@@ -328,11 +423,21 @@ k_dp(uint32_t* mlen, const uint16_t* mdist, DpScratch s, Geom g)
     if (p5 != 0xffffffffu && (p5 >> 8) <= (v5 >> 8)) v6 = ((p5 >> 8) << 8) | ((p5 & 255u) - 32u);
     uint32_t v7 = v6;
     if (p6b != 0xffffffffu && (p6b >> 8) <= (v6 >> 8)) v7 = ((p6b >> 8) << 8) | ((p6b & 255u) - 64u);
-    if (i < n)
+    if (exists)
     {
-      s.cost[b + i] = cur; s.st5[b + i] = v5; s.st6[b + i] = v6; s.st7[b + i] = v7;
-      if (priced) mlen[b + i] = keep;
+      if (i0 >= hi)
+      {
+        // warm-up zone: private overlay
+        const uint32_t k = i - hi;
+        ovl.cost[k] = cur; ovl.st5[k] = v5; ovl.st6[k] = v6; ovl.st7[k] = v7;
+      }
+      else
+      {
+        s.cost[b + i] = cur; s.st5[b + i] = v5; s.st6[b + i] = v6; s.st7[b + i] = v7;
+        if (priced) mfin[b + i] = keep;
+      }
     }
+    if (i0 == hi) ub_hi = until_bump;                            // everything at or beyond hi is done
     const uint32_t slot = i & (kDpRing - 1);
     r_cost[slot] = cur; r_st5[slot] = v5; r_st6[slot] = v6; r_st7[slot] = v7;
     p6b = p6a; p6a = v6; p5 = v5;
@@ -340,7 +445,127 @@ k_dp(uint32_t* mlen, const uint16_t* mdist, DpScratch s, Geom g)
     have_prev = true;
     __syncwarp();
   }
+  ub_lo = until_bump;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Segment-parallel DP.  The recurrence is sequential, but its state (cost differences over the
+// span later positions can reach, and the literal-run counter) forgets a wrong start within a few
+// dozen positions.  So a block is cut into segments where no match crosses (k_dp_plan), every
+// segment is priced by its own warp starting kDpWarm positions to its right from a cold state
+// (k_dp_spec), and k_dp_verify then walks the boundaries from the block end to its start: if the
+// costs a segment assumed over the span [hi, reach] differ from its right neighbour's true ones
+// only by a constant, and the literal counter agrees, its decisions are the reference's (the
+// recurrence only uses differences); otherwise that segment is priced again from the true state.
+// Exactness never depends on the guess -- only the speed does.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32)
+k_dp_plan(const uint32_t* mlen, DpTask* tasks, uint32_t* task_count, uint32_t max_seg, Geom g)
+{
+  const uint32_t j = blockIdx.x;
+  if (j >= g.n_blocks) return;
+  const uint32_t b = block_begin(g, j), n = block_len(g, j);
+  const uint32_t lane = threadIdx.x;
+  DpTask* out = tasks + (size_t)j * max_seg;
+  if (n <= kEndNoMatch) { if (lane == 0) task_count[j] = 0; return; }     // smallz4.h:755
+  uint32_t count = 0, last = 0, reach = 0;
+  uint32_t Mn = lane < n ? mlen[b + lane] : 0;
+  for (uint32_t x0 = 0; x0 < n; x0 += 32)
+  {
+    const uint32_t i = x0 + lane;
+    const uint32_t M = Mn;
+    if (i + 32 < n) Mn = mlen[b + i + 32];
+    if (x0 > 0 && x0 - last >= kDpSeg && x0 + 64 <= n && reach <= x0 + kDpSlack && count + 2 < max_seg)
+    {
+      if (lane == 0) { DpTask t; t.lo = last; t.hi = x0; t.reach = reach; t.pad_ = 0; out[count] = t; }
+      count++;
+      last = x0;
+    }
+    const uint32_t r = (i < n && M > 1) ? i + M : 0;
+    reach = max(reach, __reduce_max_sync(0xffffffffu, r));
+  }
+  if (lane == 0) { DpTask t; t.lo = last; t.hi = n; t.reach = n; t.pad_ = 0; out[count] = t; task_count[j] = count + 1; }
+}
+
+__device__ __forceinline__ DpOverlay overlay_of(uint32_t* base, uint32_t task_index)
+{
+  DpOverlay o;
+  o.cost = base + (size_t)task_index * 4 * kDpOvl;
+  o.st5 = o.cost + kDpOvl; o.st6 = o.st5 + kDpOvl; o.st7 = o.st6 + kDpOvl;
+  return o;
+}
+
+__global__ void __launch_bounds__(32)
+k_dp_spec(const uint32_t* mlen, const uint16_t* mdist, uint32_t* mfin, DpScratch s, const DpTask* tasks,
+          const uint32_t* task_count, DpState* states, uint32_t* overlays, uint32_t max_seg, Geom g)
+{
+  SZ4_DYN_SMEM(smem);
+  const uint32_t j = blockIdx.x / max_seg, k = blockIdx.x % max_seg;
+  if (j >= g.n_blocks || k >= task_count[j]) return;
+  const DpTask t = tasks[blockIdx.x];
+  uint32_t ub_hi, ub_lo;
+  dp_segment(mlen, mdist, mfin, s, overlay_of(overlays, blockIdx.x), block_begin(g, j), block_len(g, j), t.lo, t.hi,
+             false, 0, smem, ub_hi, ub_lo);
+  if (threadIdx.x == 0) { DpState st; st.ub_hi = ub_hi; st.ub_lo = ub_lo; st.redone = 0; st.cum = 0; states[blockIdx.x] = st; }
+}
+
+__global__ void __launch_bounds__(32)
+k_dp_verify(const uint32_t* mlen, const uint16_t* mdist, uint32_t* mfin, DpScratch s, const DpTask* tasks,
+            const uint32_t* task_count, DpState* states, uint32_t* overlays, uint32_t max_seg, uint32_t* redo_count, Geom g)
+{
+  SZ4_DYN_SMEM(smem);
+  const uint32_t j = blockIdx.x;
+  if (j >= g.n_blocks) return;
+  const uint32_t cnt = task_count[j];
+  if (cnt < 2) return;
+  const uint32_t b = block_begin(g, j), n = block_len(g, j);
+  const uint32_t lane = threadIdx.x;
+  uint32_t cum = 0;                                              // costs of the segment to the right minus true costs: 0 at the top
+  for (int32_t k = (int32_t)cnt - 2; k >= 0; k--)
+  {
+    const uint32_t idx = j * max_seg + (uint32_t)k;
+    const DpTask t = tasks[idx];
+    DpState st = states[idx];
+    const DpState right = states[idx + 1];
+    const DpOverlay o = overlay_of(overlays, idx);
+    // the span positions left of hi can look at: [hi, max(hi, reach)]
+    const uint32_t span = (t.reach > t.hi ? t.reach - t.hi : 0) + 1;
+    const uint32_t delta = __ldcg(s.cost + b + t.hi) - __ldcg(o.cost);
+    bool same = st.ub_hi == right.ub_lo && span <= kDpWarm;
+    for (uint32_t y = lane; y < span && y < kDpOvl; y += 32)
+      if (__ldcg(s.cost + b + t.hi + y) - __ldcg(o.cost + y) != delta) same = false;
+    same = __all_sync(0xffffffffu, same);
+    if (same)
+    {
+      // costs of this segment = costs in the right neighbour's frame - delta
+      cum = cum - delta;
+      st.cum = cum;
+    }
+    else
+    {
+      uint32_t ub_hi, ub_lo;
+      dp_segment(mlen, mdist, mfin, s, o, b, n, t.lo, t.hi, true, right.ub_lo, smem, ub_hi, ub_lo);
+      st.ub_lo = ub_lo; st.redone = 1; st.cum = cum;
+      if (lane == 0) atomicAdd(redo_count, 1u);
+    }
+    if (lane == 0) states[idx] = st;
+    __syncwarp();
+  }
+}
+
+// debug only: bring every segment's costs into the true frame (they differ by a constant per segment)
+__global__ void __launch_bounds__(256)
+k_dp_cost_fix(DpScratch s, const DpTask* tasks, const uint32_t* task_count, const DpState* states, uint32_t max_seg, Geom g)
+{
+  const uint32_t j = blockIdx.x / max_seg, k = blockIdx.x % max_seg;
+  if (j >= g.n_blocks || k >= task_count[j]) return;
+  const DpTask t = tasks[blockIdx.x];
+  const uint32_t cum = states[blockIdx.x].cum;
+  if (cum == 0) return;
+  const uint32_t b = block_begin(g, j);
+  for (uint32_t y = t.lo + threadIdx.x; y < t.hi; y += blockDim.x) s.cost[b + y] -= cum;
+}
+
 
 // ---------------------------------------------------------------------------------------------
 // Walk the chosen parse from the start of the block and list its sequences.

@@ -56,8 +56,10 @@ struct sz4_ctx
   // device memory (grow-only)
   DevBuf data, ph, pe, mlen, mdist, scratch, hist, hist_scanned, partials, seqs, seq_count, packed,
          saved_ph, saved_pe, seeds, nseeds, seg, block_out, seg_total, dbg_len, dbg_dist, scalar_state,
-         run_fwd, ones_back, flag_last, flag_carry;
-  unsigned long long* h_seg_total = nullptr;    // pinned
+         run_fwd, ones_back, flag_last, flag_carry, mfin, dp_tasks, dp_count, dp_states, dp_overlays, dp_redo;
+  unsigned long long* h_seg_total = nullptr;    // pinned: [0] segment bytes, [1] DP segments priced twice
+  unsigned long long dp_redos = 0, dp_segments = 0;
+  bool               dp_ran = false;
   // stats
   double             kernel_ms = 0;
   unsigned long long launches = 0;
@@ -261,17 +263,42 @@ static int run_batch(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
   dp.st5 = dp.cost + N + 64;
   dp.st6 = dp.st5 + N + 64;
   dp.st7 = dp.st6 + N + 64;
+  const uint32_t* final_len = mlen;
+  ctx->dp_ran = false;
   if (g.max_chain > kGreedyMax)                                   // smallz4.h:755
   {
     if (!ctx->dp_attr_set)
     {
-      CK(cudaFuncSetAttribute(k_dp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDpSmem));
+      CK(cudaFuncSetAttribute(k_dp_spec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDpSmem));
+      CK(cudaFuncSetAttribute(k_dp_verify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDpSmem));
       ctx->dp_attr_set = true;
     }
-    LAUNCH(ctx, k_dp, g.n_blocks, 32, kDpSmem, mlen, (const uint16_t*)mdist, dp, g);
+    const uint32_t max_seg = g.block_size / kDpSeg + 2;
+    const uint32_t n_tasks = g.n_blocks * max_seg;
+    RSV(mfin, ((size_t)N + kPad) * 4);
+    RSV(dp_tasks, (size_t)n_tasks * sizeof(DpTask) + 64);
+    RSV(dp_count, (size_t)g.n_blocks * 4 + 64);
+    RSV(dp_states, (size_t)n_tasks * sizeof(DpState) + 64);
+    RSV(dp_overlays, (size_t)n_tasks * 4 * kDpOvl * 4 + 64);
+    RSV(dp_redo, 64);
+    uint32_t* mfin = (uint32_t*)ctx->mfin.p;
+    // positions the DP does not price (the last five of a block, blocks of <= 12 bytes) keep what was found
+    CK(cudaMemcpyAsync(mfin, mlen, (size_t)N * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaMemsetAsync(ctx->dp_redo.p, 0, 8, ctx->stream));
+    LAUNCH(ctx, k_dp_plan, g.n_blocks, 32, 0, (const uint32_t*)mlen, (DpTask*)ctx->dp_tasks.p, (uint32_t*)ctx->dp_count.p, max_seg, g);
+    LAUNCH(ctx, k_dp_spec, n_tasks, 32, kDpSmem, (const uint32_t*)mlen, (const uint16_t*)mdist, mfin, dp, (const DpTask*)ctx->dp_tasks.p,
+           (const uint32_t*)ctx->dp_count.p, (DpState*)ctx->dp_states.p, (uint32_t*)ctx->dp_overlays.p, max_seg, g);
+    LAUNCH(ctx, k_dp_verify, g.n_blocks, 32, kDpSmem, (const uint32_t*)mlen, (const uint16_t*)mdist, mfin, dp, (const DpTask*)ctx->dp_tasks.p,
+           (const uint32_t*)ctx->dp_count.p, (DpState*)ctx->dp_states.p, (uint32_t*)ctx->dp_overlays.p, max_seg,
+           (uint32_t*)ctx->dp_redo.p, g);
+    if (ctx->debug_keep)
+      LAUNCH(ctx, k_dp_cost_fix, n_tasks, 256, 0, dp, (const DpTask*)ctx->dp_tasks.p, (const uint32_t*)ctx->dp_count.p,
+             (const DpState*)ctx->dp_states.p, max_seg, g);
+    final_len = mfin;
+    ctx->dp_ran = true;
   }
   PHASE(5);
-  LAUNCH(ctx, k_path, g.n_blocks, 32, 0, (const uint32_t*)mlen, (const uint16_t*)mdist, (SeqRec*)ctx->seqs.p, seq_stride,
+  LAUNCH(ctx, k_path, g.n_blocks, 32, 0, final_len, (const uint16_t*)mdist, (SeqRec*)ctx->seqs.p, seq_stride,
          (uint32_t*)ctx->seq_count.p, g);
   LAUNCH(ctx, k_seq_scan, g.n_blocks, 1024, 0, (SeqRec*)ctx->seqs.p, seq_stride, (const uint32_t*)ctx->seq_count.p,
          (uint32_t*)ctx->packed.p, g);
@@ -284,11 +311,13 @@ static int run_batch(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
   PHASE(7);
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
   CK(cudaMemcpyAsync(ctx->h_seg_total, ctx->seg_total.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (ctx->dp_ran) CK(cudaMemcpyAsync(ctx->h_seg_total + 1, ctx->dp_redo.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaGetLastError());
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
   ctx->kernel_ms += ms;
+  if (ctx->dp_ran) ctx->dp_redos += (uint32_t)ctx->h_seg_total[1];
   if (ctx->profile)
     for (int k = 0; k < 7; k++)
     {
@@ -467,7 +496,8 @@ void sz4_destroy(sz4_ctx* ctx)
   DevBuf* all[] = { &ctx->data, &ctx->ph, &ctx->pe, &ctx->mlen, &ctx->mdist, &ctx->scratch, &ctx->hist, &ctx->hist_scanned,
                     &ctx->partials, &ctx->seqs, &ctx->seq_count, &ctx->packed, &ctx->saved_ph, &ctx->saved_pe, &ctx->seeds,
                     &ctx->nseeds, &ctx->seg, &ctx->block_out, &ctx->seg_total, &ctx->dbg_len, &ctx->dbg_dist, &ctx->scalar_state,
-                    &ctx->run_fwd, &ctx->ones_back, &ctx->flag_last, &ctx->flag_carry };
+                    &ctx->run_fwd, &ctx->ones_back, &ctx->flag_last, &ctx->flag_carry, &ctx->mfin, &ctx->dp_tasks,
+                    &ctx->dp_count, &ctx->dp_states, &ctx->dp_overlays, &ctx->dp_redo };
   for (DevBuf* b : all) if (b->p) cudaFree(b->p);
   if (ctx->h_seg_total) cudaFreeHost(ctx->h_seg_total);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -521,7 +551,7 @@ int sz4_compress_host(sz4_ctx* ctx, const void* src, size_t n, void* dst, size_t
 {
   if (!ctx || (!src && n) || !dst || !frame_len) return SZ4_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
-  ctx->kernel_ms = 0; ctx->launches = 0;
+  ctx->kernel_ms = 0; ctx->launches = 0; ctx->dp_redos = 0;
   for (int k = 0; k < 7; k++) ctx->phase_ms[k] = 0;
   uint8_t* out = (uint8_t*)dst;
   if (cap < 16) { ctx->err = "destination too small"; return SZ4_ERR_DST_SMALL; }
@@ -565,7 +595,7 @@ int sz4_compress_device(sz4_ctx* ctx, const void* d_src, size_t halo, size_t n, 
   if (!ctx || !d_src || !d_dst || !segment_len || max_chain == 0) return SZ4_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
   (void)cuda_stream;   // work is ordered on the context's stream; the caller's stream is synchronised by the blocking return
-  ctx->kernel_ms = 0; ctx->launches = 0;
+  ctx->kernel_ms = 0; ctx->launches = 0; ctx->dp_redos = 0;
   for (int k = 0; k < 7; k++) ctx->phase_ms[k] = 0;
   StreamJob job;
   job.src = (const uint8_t*)d_src; job.src_on_device = true; job.halo_in_src = halo; job.n = n;
@@ -607,6 +637,8 @@ int sz4_last_stats(const sz4_ctx* ctx, double* kernel_ms, unsigned long long* la
   return SZ4_OK;
 }
 
+long long sz4_last_dp_redos(const sz4_ctx* ctx) { return ctx ? (long long)ctx->dp_redos : -1; }
+
 int sz4_last_phase_ms(const sz4_ctx* ctx, double* out7)
 {
   if (!ctx || !out7) return SZ4_ERR_ARG;
@@ -624,7 +656,7 @@ int sz4_debug_fetch(sz4_ctx* ctx, const char* what, void* dst, size_t count)
   else if (!strcmp(what, "ph")) { src = (uint16_t*)ctx->ph.p + kPad; elem = 2; }
   else if (!strcmp(what, "len_found")) { src = ctx->dbg_len.p; elem = 4; }
   else if (!strcmp(what, "dist_found")) { src = ctx->dbg_dist.p; elem = 2; }
-  else if (!strcmp(what, "len_final")) { src = ctx->mlen.p; elem = 4; }
+  else if (!strcmp(what, "len_final")) { src = ctx->dp_ran ? ctx->mfin.p : ctx->mlen.p; elem = 4; }
   else if (!strcmp(what, "dist_final")) { src = ctx->mdist.p; elem = 2; }
   else if (!strcmp(what, "cost")) { src = ctx->scratch.p; elem = 4; }
   if (!src) { ctx->err = "unknown array"; return SZ4_ERR_ARG; }
