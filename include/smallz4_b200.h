@@ -92,6 +92,7 @@ int sz4_last_phase_ms(const sz4_ctx* ctx, double* out7);
 
 /* segments of the cost DP that failed verification in the last call and were priced again */
 long long sz4_last_dp_redos(const sz4_ctx* ctx);
+long long sz4_last_path_redos(const sz4_ctx* ctx);   /* same for the segments of the parse walk */
 
 /* test hook: copy an intermediate array of the last batch to the host (needs option debug_keep=1).
    what: "pe" u16, "len_found" u32, "dist_found" u16, "len_final" u32, "cost" u32; count = elements */

@@ -56,6 +56,7 @@ def load_library(path=None):
     lib.sz4_last_stats.restype = i32
     lib.sz4_last_phase_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]; lib.sz4_last_phase_ms.restype = i32
     lib.sz4_last_dp_redos.argtypes = [vp]; lib.sz4_last_dp_redos.restype = ctypes.c_longlong
+    lib.sz4_last_path_redos.argtypes = [vp]; lib.sz4_last_path_redos.restype = ctypes.c_longlong
     lib.sz4_debug_fetch.argtypes = [vp, ctypes.c_char_p, vp, sz]; lib.sz4_debug_fetch.restype = i32
     return lib
 
@@ -154,6 +155,9 @@ class Compressor:
 
     def last_dp_redos(self):
         return self.lib.sz4_last_dp_redos(self.h)
+
+    def last_path_redos(self):
+        return self.lib.sz4_last_path_redos(self.h)
 
     def debug_fetch(self, what, count):
         dt = {"pe": np.uint16, "ph": np.uint16, "len_found": np.uint32, "dist_found": np.uint16,

@@ -459,30 +459,77 @@ __device__ __forceinline__ void dp_segment(const uint32_t* mlen, const uint16_t*
 // recurrence only uses differences); otherwise that segment is priced again from the true state.
 // Exactness never depends on the guess -- only the speed does.
 // ---------------------------------------------------------------------------------------------
+// reach of every group of 32 positions: max over its positions of (position + found match length), 0 if none.
+// One warp per 1024 positions; lane g ends up with the value of group g and the 32 values are stored coalesced.
+__global__ void __launch_bounds__(256)
+k_dp_group_reach(const uint32_t* mlen, uint32_t* group_reach, uint32_t groups_per_block, Geom g)
+{
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const uint32_t chunks_per_block = (groups_per_block + 31) / 32;
+  const uint32_t j = warp / chunks_per_block, c = warp % chunks_per_block;
+  if (j >= g.n_blocks) return;
+  const uint32_t b = block_begin(g, j), n = block_len(g, j);
+  uint32_t mine = 0;
+#pragma unroll 4
+  for (uint32_t k = 0; k < 32; k++)
+  {
+    const uint32_t i = (c * 32 + k) * 32 + lane;
+    uint32_t r = 0;
+    if (i < n) { const uint32_t M = mlen[b + i]; if (M > 1) r = i + M; }
+    r = __reduce_max_sync(0xffffffffu, r);
+    if (lane == k) mine = r;
+  }
+  const uint32_t grp = c * 32 + lane;
+  if (grp < groups_per_block) group_reach[(size_t)j * groups_per_block + grp] = mine;
+}
+
+// One warp per block: exclusive prefix maximum of the group reaches, 32 groups per step, and a boundary
+// wherever the segment is long enough and nothing from the left reaches more than kDpSlack beyond it.
 __global__ void __launch_bounds__(32)
-k_dp_plan(const uint32_t* mlen, DpTask* tasks, uint32_t* task_count, uint32_t max_seg, Geom g)
+k_dp_plan(const uint32_t* group_reach, uint32_t groups_per_block, DpTask* tasks, uint32_t* task_count, uint32_t max_seg, Geom g)
 {
   const uint32_t j = blockIdx.x;
   if (j >= g.n_blocks) return;
-  const uint32_t b = block_begin(g, j), n = block_len(g, j);
+  const uint32_t n = block_len(g, j);
   const uint32_t lane = threadIdx.x;
   DpTask* out = tasks + (size_t)j * max_seg;
   if (n <= kEndNoMatch) { if (lane == 0) task_count[j] = 0; return; }     // smallz4.h:755
-  uint32_t count = 0, last = 0, reach = 0;
-  uint32_t Mn = lane < n ? mlen[b + lane] : 0;
-  for (uint32_t x0 = 0; x0 < n; x0 += 32)
+  const uint32_t* gr = group_reach + (size_t)j * groups_per_block;
+  const uint32_t groups = (n + 31) / 32;
+  uint32_t count = 0, last = 0, carry = 0;
+  uint32_t nxt = lane < groups ? gr[lane] : 0;
+  for (uint32_t g0 = 0; g0 < groups; g0 += 32)
   {
-    const uint32_t i = x0 + lane;
-    const uint32_t M = Mn;
-    if (i + 32 < n) Mn = mlen[b + i + 32];
-    if (x0 > 0 && x0 - last >= kDpSeg && x0 + 64 <= n && reach <= x0 + kDpSlack && count + 2 < max_seg)
+    const uint32_t mine = nxt;
+    if (g0 + 32 + lane < groups) nxt = gr[g0 + 32 + lane]; else nxt = 0;
+    // inclusive prefix max over the 32 groups, then shift by one lane: reach of everything left of group g0+lane
+    uint32_t incl = mine;
+#pragma unroll
+    for (uint32_t d = 1; d < 32; d <<= 1)
     {
-      if (lane == 0) { DpTask t; t.lo = last; t.hi = x0; t.reach = reach; t.pad_ = 0; out[count] = t; }
-      count++;
-      last = x0;
+      uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl = max(incl, t);
     }
-    const uint32_t r = (i < n && M > 1) ? i + M : 0;
-    reach = max(reach, __reduce_max_sync(0xffffffffu, r));
+    uint32_t before = __shfl_up_sync(0xffffffffu, incl, 1);
+    before = lane == 0 ? carry : max(before, carry);
+    const uint32_t x0 = (g0 + lane) * 32;
+    const bool fits = g0 + lane < groups && x0 > 0 && x0 + 64 <= n && before <= x0 + kDpSlack;
+    // at most a few boundaries per 1024 positions: take them in order
+    uint32_t cand = __ballot_sync(0xffffffffu, fits);
+    while (cand)
+    {
+      const int l = __ffs((int)cand) - 1;
+      const uint32_t xb = (g0 + (uint32_t)l) * 32;
+      cand &= cand - 1;
+      if (xb - last >= kDpSeg && count + 2 < max_seg)
+      {
+        const uint32_t reach = __shfl_sync(0xffffffffu, before, l);
+        if (lane == 0) { DpTask t; t.lo = last; t.hi = xb; t.reach = reach; t.pad_ = 0; out[count] = t; }
+        count++;
+        last = xb;
+      }
+    }
+    carry = max(carry, __shfl_sync(0xffffffffu, incl, 31));
   }
   if (lane == 0) { DpTask t; t.lo = last; t.hi = n; t.reach = n; t.pad_ = 0; out[count] = t; task_count[j] = count + 1; }
 }
@@ -598,23 +645,29 @@ __device__ __forceinline__ void path_load(const uint32_t* mlen, const uint16_t* 
   }
 }
 
-__global__ void __launch_bounds__(32)
-k_path(const uint32_t* mlen, const uint16_t* mdist, SeqRec* seqs, uint32_t seq_stride, uint32_t* seq_count, Geom g)
-{
-  const uint32_t j = blockIdx.x;
-  if (j >= g.n_blocks) return;
-  const uint32_t b = block_begin(g, j), n = block_len(g, j);
-  const uint32_t lane = threadIdx.x;
-  SeqRec* out = seqs + (size_t)j * seq_stride;
+#ifndef SZ4_PATH_SEG
+#define SZ4_PATH_SEG 32768
+#endif
+#ifndef SZ4_PATH_WARM
+#define SZ4_PATH_WARM 2048
+#endif
+enum : uint32_t { kPathSeg = SZ4_PATH_SEG, kPathWarm = SZ4_PATH_WARM };
 
-  uint32_t at = 0;            // current position on the path (block relative)
-  uint32_t count = 0;
+// Walk the parse from position `from` up to (not including) `hi` and list the matches that start in [lo, hi).
+//   cover   = end of the last match that starts before lo  (so the walk enters [lo, hi) at max(lo, cover))
+//   leave   = end of the last match that starts before hi  (so it leaves at max(hi, leave))
+__device__ __forceinline__ void path_walk(const uint32_t* mlen, const uint16_t* mdist, uint32_t b, uint32_t n, uint32_t from,
+                                          uint32_t lo, uint32_t hi, SeqRec* out, uint32_t& count, uint32_t& cover, uint32_t& leave)
+{
+  const uint32_t lane = threadIdx.x;
+  uint32_t at = from;         // current position on the path (block relative)
+  count = 0; cover = 0; leave = 0;
   // the walk reads 128 positions at a time and keeps the following 256 in flight (two sets of registers,
   // enough to cover a DRAM round trip); it only lists the matches on the path -- sizes and output
   // offsets are computed in parallel afterwards (k_seq_scan)
   uint32_t cur_sw = 0xffffffffu, n1_sw = 0xffffffffu, n2_sw = 0xffffffffu;
   uint32_t Lc[4], Dc[4], L1[4], D1[4], L2[4], D2[4];
-  while (at < n)
+  while (at < hi)
   {
     const uint32_t sw = at & ~127u;
     if (sw != cur_sw)
@@ -653,19 +706,109 @@ k_path(const uint32_t* mlen, const uint16_t* mdist, SeqRec* seqs, uint32_t seq_s
       const uint32_t m = is_match & (0xffffffffu << o);
       if (m == 0) { at = w + 32; break; }
       const int ml = __ffs((int)m) - 1;
+      const uint32_t pos = w + (uint32_t)ml;
+      if (pos >= hi) { at = hi; break; }
       const uint32_t len = __shfl_sync(0xffffffffu, L, ml);
       const uint32_t dist = __shfl_sync(0xffffffffu, Dd, ml);
-      const uint32_t pos = w + (uint32_t)ml;
-      if (lane == 0) { SeqRec r; r.pos = pos; r.len = len; r.dist = dist; r.out = 0; out[count] = r; }
-      count++;
+      if (pos >= lo)
+      {
+        if (lane == 0) { SeqRec r; r.pos = pos; r.len = len; r.dist = dist; r.out = 0; out[count] = r; }
+        count++;
+      }
+      else cover = pos + len;
+      leave = pos + len;
       at = pos + len;
       o = at - w;                      // may be >= 32: leaves the window
     }
   }
-  // final literals (smallz4.h:292-308: the last token has no match)
-  if (lane == 0) { SeqRec r; r.pos = n; r.len = 0; r.dist = 0; r.out = 0; out[count] = r; }
-  count++;
-  if (lane == 0) seq_count[j] = count;
+}
+
+// Per block, the parse is walked in fixed segments of kPathSeg positions.  A walk started at an arbitrary
+// position joins the true path as soon as both land on the same position, so every segment starts
+// kPathWarm positions early (k_path_spec); k_path_join then goes through the segments in order: a
+// segment whose assumed entry point equals the true one (where the segment before it left) is kept,
+// otherwise it is walked again from the true entry.  k_path_compact makes the record list contiguous.
+struct PathSeg { uint32_t entry, leave, count, base; };
+
+__device__ __forceinline__ SeqRec* path_seg_records(SeqRec* tmp, uint32_t seq_stride, uint32_t j, uint32_t k, uint32_t min_len)
+{
+  return tmp + (size_t)j * seq_stride + (size_t)k * (kPathSeg / min_len + 1);
+}
+
+__global__ void __launch_bounds__(32)
+k_path_spec(const uint32_t* mlen, const uint16_t* mdist, SeqRec* tmp, uint32_t seq_stride, PathSeg* segs, uint32_t max_seg,
+            uint32_t min_len, Geom g)
+{
+  const uint32_t j = blockIdx.x / max_seg, k = blockIdx.x % max_seg;
+  if (j >= g.n_blocks) return;
+  const uint32_t b = block_begin(g, j), n = block_len(g, j);
+  const uint32_t lo = k * kPathSeg;
+  if (lo >= n && !(k == 0 && n == 0)) return;
+  const uint32_t hi = min(lo + (uint32_t)kPathSeg, n);
+  const uint32_t from = lo > kPathWarm ? lo - kPathWarm : 0;
+  uint32_t count, cover, leave;
+  path_walk(mlen, mdist, b, n, from, lo, hi, path_seg_records(tmp, seq_stride, j, k, min_len), count, cover, leave);
+  if (threadIdx.x == 0)
+  {
+    PathSeg ps; ps.entry = max(lo, cover); ps.leave = max(hi, leave); ps.count = count; ps.base = 0;
+    segs[blockIdx.x] = ps;
+  }
+}
+
+__global__ void __launch_bounds__(32)
+k_path_join(const uint32_t* mlen, const uint16_t* mdist, SeqRec* tmp, uint32_t seq_stride, PathSeg* segs, uint32_t max_seg,
+            uint32_t min_len, uint32_t* seq_count, uint32_t* redo_count, Geom g)
+{
+  const uint32_t j = blockIdx.x;
+  if (j >= g.n_blocks) return;
+  const uint32_t b = block_begin(g, j), n = block_len(g, j);
+  const uint32_t lane = threadIdx.x;
+  const uint32_t nseg = (n + kPathSeg - 1) / kPathSeg;
+  uint32_t entry = 0, base = 0;                                  // true entry into the next segment; records so far
+  for (uint32_t k = 0; k < nseg; k++)
+  {
+    const uint32_t idx = j * max_seg + k;
+    PathSeg ps = segs[idx];
+    const uint32_t lo = k * kPathSeg, hi = min(lo + (uint32_t)kPathSeg, n);
+    if (ps.entry != entry)
+    {
+      if (entry >= hi) { ps.count = 0; ps.leave = entry; }       // a match jumps over the whole segment
+      else
+      {
+        uint32_t count, cover, leave;
+        path_walk(mlen, mdist, b, n, entry, lo, hi, path_seg_records(tmp, seq_stride, j, k, min_len), count, cover, leave);
+        ps.count = count; ps.leave = max(hi, leave);
+      }
+      ps.entry = entry;
+      if (lane == 0) atomicAdd(redo_count + 1, 1u);
+    }
+    ps.base = base;
+    if (lane == 0) segs[idx] = ps;
+    base += ps.count;
+    entry = ps.leave;
+    __syncwarp();
+  }
+  if (lane == 0) seq_count[j] = base + 1;                        // + the final literals
+}
+
+__global__ void __launch_bounds__(128)
+k_path_compact(const SeqRec* tmp, SeqRec* seqs, uint32_t seq_stride, const PathSeg* segs, uint32_t max_seg, uint32_t min_len,
+               const uint32_t* seq_count, Geom g)
+{
+  const uint32_t j = blockIdx.x / max_seg, k = blockIdx.x % max_seg;
+  if (j >= g.n_blocks) return;
+  const uint32_t n = block_len(g, j);
+  SeqRec* out = seqs + (size_t)j * seq_stride;
+  if (k == 0 && threadIdx.x == 0)
+  {
+    // final literals (smallz4.h:292-308: the last token has no match)
+    SeqRec r; r.pos = n; r.len = 0; r.dist = 0; r.out = 0;
+    out[seq_count[j] - 1] = r;
+  }
+  if (k * kPathSeg >= n) return;
+  const PathSeg ps = segs[blockIdx.x];
+  const SeqRec* src = tmp + (size_t)j * seq_stride + (size_t)k * (kPathSeg / min_len + 1);
+  for (uint32_t t = threadIdx.x; t < ps.count; t += blockDim.x) out[ps.base + t] = src[t];
 }
 
 // Offsets of the sequences inside the compressed block = exclusive prefix sum of their sizes

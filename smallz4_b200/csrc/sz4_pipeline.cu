@@ -56,9 +56,9 @@ struct sz4_ctx
   // device memory (grow-only)
   DevBuf data, ph, pe, mlen, mdist, scratch, hist, hist_scanned, partials, seqs, seq_count, packed,
          saved_ph, saved_pe, seeds, nseeds, seg, block_out, seg_total, dbg_len, dbg_dist, scalar_state,
-         run_fwd, ones_back, flag_last, flag_carry, mfin, dp_tasks, dp_count, dp_states, dp_overlays, dp_redo;
+         run_fwd, ones_back, flag_last, flag_carry, mfin, dp_tasks, dp_count, dp_states, dp_overlays, dp_redo, dp_reach, seqs_tmp, path_segs;
   unsigned long long* h_seg_total = nullptr;    // pinned: [0] segment bytes, [1] DP segments priced twice
-  unsigned long long dp_redos = 0, dp_segments = 0;
+  unsigned long long dp_redos = 0, path_redos = 0;
   bool               dp_ran = false;
   // stats
   double             kernel_ms = 0;
@@ -136,7 +136,7 @@ static int run_batch(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
   const uint32_t max_seeds = N / 65000 + g.n_blocks + 16;
   RSV(seeds, (size_t)max_seeds * sizeof(Seed));
   // a sequence ends with a match of >= 4 bytes (>= 2 with a dictionary, DESIGN.md Q-dict)
-  const uint32_t seq_stride = g.block_size / (g.shift ? 2 : 4) + 8;
+  const uint32_t seq_stride = (g.block_size / kPathSeg + 1) * (kPathSeg / (g.shift ? 2 : 4) + 1) + 8;
   RSV(seqs, (size_t)g.n_blocks * seq_stride * sizeof(SeqRec));
   const uint64_t per_block_out = g.legacy ? (uint64_t)g.block_size + g.block_size / 255 + 64 : (uint64_t)g.block_size;
   const uint64_t seg_cap = (uint64_t)g.n_blocks * (per_block_out + 4) + 64;
@@ -265,6 +265,8 @@ static int run_batch(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
   dp.st7 = dp.st6 + N + 64;
   const uint32_t* final_len = mlen;
   ctx->dp_ran = false;
+  RSV(dp_redo, 64);
+  CK(cudaMemsetAsync(ctx->dp_redo.p, 0, 8, ctx->stream));
   if (g.max_chain > kGreedyMax)                                   // smallz4.h:755
   {
     if (!ctx->dp_attr_set)
@@ -280,12 +282,15 @@ static int run_batch(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
     RSV(dp_count, (size_t)g.n_blocks * 4 + 64);
     RSV(dp_states, (size_t)n_tasks * sizeof(DpState) + 64);
     RSV(dp_overlays, (size_t)n_tasks * 4 * kDpOvl * 4 + 64);
-    RSV(dp_redo, 64);
     uint32_t* mfin = (uint32_t*)ctx->mfin.p;
     // positions the DP does not price (the last five of a block, blocks of <= 12 bytes) keep what was found
     CK(cudaMemcpyAsync(mfin, mlen, (size_t)N * 4, cudaMemcpyDeviceToDevice, ctx->stream));
-    CK(cudaMemsetAsync(ctx->dp_redo.p, 0, 8, ctx->stream));
-    LAUNCH(ctx, k_dp_plan, g.n_blocks, 32, 0, (const uint32_t*)mlen, (DpTask*)ctx->dp_tasks.p, (uint32_t*)ctx->dp_count.p, max_seg, g);
+    const uint32_t groups_per_block = g.block_size / 32;
+    RSV(dp_reach, (size_t)g.n_blocks * groups_per_block * 4 + 64);
+    LAUNCH(ctx, k_dp_group_reach, div_up((uint64_t)g.n_blocks * div_up(groups_per_block, 32) * 32, 256), 256, 0,
+           (const uint32_t*)mlen, (uint32_t*)ctx->dp_reach.p, groups_per_block, g);
+    LAUNCH(ctx, k_dp_plan, g.n_blocks, 32, 0, (const uint32_t*)ctx->dp_reach.p, groups_per_block, (DpTask*)ctx->dp_tasks.p,
+           (uint32_t*)ctx->dp_count.p, max_seg, g);
     LAUNCH(ctx, k_dp_spec, n_tasks, 32, kDpSmem, (const uint32_t*)mlen, (const uint16_t*)mdist, mfin, dp, (const DpTask*)ctx->dp_tasks.p,
            (const uint32_t*)ctx->dp_count.p, (DpState*)ctx->dp_states.p, (uint32_t*)ctx->dp_overlays.p, max_seg, g);
     LAUNCH(ctx, k_dp_verify, g.n_blocks, 32, kDpSmem, (const uint32_t*)mlen, (const uint16_t*)mdist, mfin, dp, (const DpTask*)ctx->dp_tasks.p,
@@ -298,8 +303,18 @@ static int run_batch(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
     ctx->dp_ran = true;
   }
   PHASE(5);
-  LAUNCH(ctx, k_path, g.n_blocks, 32, 0, final_len, (const uint16_t*)mdist, (SeqRec*)ctx->seqs.p, seq_stride,
-         (uint32_t*)ctx->seq_count.p, g);
+  {
+    const uint32_t min_len = g.shift ? 2 : 4;
+    const uint32_t max_pseg = g.block_size / kPathSeg + 1;
+    RSV(seqs_tmp, (size_t)g.n_blocks * seq_stride * sizeof(SeqRec));
+    RSV(path_segs, (size_t)g.n_blocks * max_pseg * sizeof(PathSeg) + 64);
+    LAUNCH(ctx, k_path_spec, g.n_blocks * max_pseg, 32, 0, final_len, (const uint16_t*)mdist, (SeqRec*)ctx->seqs_tmp.p, seq_stride,
+           (PathSeg*)ctx->path_segs.p, max_pseg, min_len, g);
+    LAUNCH(ctx, k_path_join, g.n_blocks, 32, 0, final_len, (const uint16_t*)mdist, (SeqRec*)ctx->seqs_tmp.p, seq_stride,
+           (PathSeg*)ctx->path_segs.p, max_pseg, min_len, (uint32_t*)ctx->seq_count.p, (uint32_t*)ctx->dp_redo.p, g);
+    LAUNCH(ctx, k_path_compact, g.n_blocks * max_pseg, 128, 0, (const SeqRec*)ctx->seqs_tmp.p, (SeqRec*)ctx->seqs.p, seq_stride,
+           (const PathSeg*)ctx->path_segs.p, max_pseg, min_len, (const uint32_t*)ctx->seq_count.p, g);
+  }
   LAUNCH(ctx, k_seq_scan, g.n_blocks, 1024, 0, (SeqRec*)ctx->seqs.p, seq_stride, (const uint32_t*)ctx->seq_count.p,
          (uint32_t*)ctx->packed.p, g);
   PHASE(6);
@@ -311,13 +326,14 @@ static int run_batch(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
   PHASE(7);
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
   CK(cudaMemcpyAsync(ctx->h_seg_total, ctx->seg_total.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
-  if (ctx->dp_ran) CK(cudaMemcpyAsync(ctx->h_seg_total + 1, ctx->dp_redo.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->h_seg_total + 1, ctx->dp_redo.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaGetLastError());
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
   ctx->kernel_ms += ms;
-  if (ctx->dp_ran) ctx->dp_redos += (uint32_t)ctx->h_seg_total[1];
+  ctx->dp_redos += (uint32_t)ctx->h_seg_total[1];
+  ctx->path_redos += (uint32_t)(ctx->h_seg_total[1] >> 32);
   if (ctx->profile)
     for (int k = 0; k < 7; k++)
     {
@@ -497,7 +513,8 @@ void sz4_destroy(sz4_ctx* ctx)
                     &ctx->partials, &ctx->seqs, &ctx->seq_count, &ctx->packed, &ctx->saved_ph, &ctx->saved_pe, &ctx->seeds,
                     &ctx->nseeds, &ctx->seg, &ctx->block_out, &ctx->seg_total, &ctx->dbg_len, &ctx->dbg_dist, &ctx->scalar_state,
                     &ctx->run_fwd, &ctx->ones_back, &ctx->flag_last, &ctx->flag_carry, &ctx->mfin, &ctx->dp_tasks,
-                    &ctx->dp_count, &ctx->dp_states, &ctx->dp_overlays, &ctx->dp_redo };
+                    &ctx->dp_count, &ctx->dp_states, &ctx->dp_overlays, &ctx->dp_redo, &ctx->dp_reach, &ctx->seqs_tmp,
+                    &ctx->path_segs };
   for (DevBuf* b : all) if (b->p) cudaFree(b->p);
   if (ctx->h_seg_total) cudaFreeHost(ctx->h_seg_total);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -551,7 +568,7 @@ int sz4_compress_host(sz4_ctx* ctx, const void* src, size_t n, void* dst, size_t
 {
   if (!ctx || (!src && n) || !dst || !frame_len) return SZ4_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
-  ctx->kernel_ms = 0; ctx->launches = 0; ctx->dp_redos = 0;
+  ctx->kernel_ms = 0; ctx->launches = 0; ctx->dp_redos = 0; ctx->path_redos = 0;
   for (int k = 0; k < 7; k++) ctx->phase_ms[k] = 0;
   uint8_t* out = (uint8_t*)dst;
   if (cap < 16) { ctx->err = "destination too small"; return SZ4_ERR_DST_SMALL; }
@@ -595,7 +612,7 @@ int sz4_compress_device(sz4_ctx* ctx, const void* d_src, size_t halo, size_t n, 
   if (!ctx || !d_src || !d_dst || !segment_len || max_chain == 0) return SZ4_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
   (void)cuda_stream;   // work is ordered on the context's stream; the caller's stream is synchronised by the blocking return
-  ctx->kernel_ms = 0; ctx->launches = 0; ctx->dp_redos = 0;
+  ctx->kernel_ms = 0; ctx->launches = 0; ctx->dp_redos = 0; ctx->path_redos = 0;
   for (int k = 0; k < 7; k++) ctx->phase_ms[k] = 0;
   StreamJob job;
   job.src = (const uint8_t*)d_src; job.src_on_device = true; job.halo_in_src = halo; job.n = n;
@@ -638,6 +655,7 @@ int sz4_last_stats(const sz4_ctx* ctx, double* kernel_ms, unsigned long long* la
 }
 
 long long sz4_last_dp_redos(const sz4_ctx* ctx) { return ctx ? (long long)ctx->dp_redos : -1; }
+long long sz4_last_path_redos(const sz4_ctx* ctx) { return ctx ? (long long)ctx->path_redos : -1; }
 
 int sz4_last_phase_ms(const sz4_ctx* ctx, double* out7)
 {
