@@ -242,10 +242,21 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
   v.s_data = smem_base(s_data);
   v.s_pe = smem_base(s_pe);
 
-  if (threadIdx.x == 0) next_pos = 0;
+  // the one position of the tile (if any) whose chain entry was zeroed by the next block's lookback (Q-twice)
+  __shared__ uint32_t tw_pos_s;
+  if (threadIdx.x == 0)
+  {
+    next_pos = t0;
+    uint32_t tw = 0xffffffffu;
+    const uint32_t cand = block_end(g, j) - kEndNoMatch;
+    if (block_len(g, j) >= kEndNoMatch && cand >= t0 && cand < t1 && is_twice_inserted(g, cand)) tw = cand;
+    tw_pos_s = tw;
+  }
   stage_two(s_data, data + v.dlo, v.dhi - v.dlo, (unsigned char*)s_pe, (const unsigned char*)(pe + v.clo),
             (chi - v.clo) * 2, &bar, use_bulk);
   __syncthreads();
+  const uint32_t tw_pos = tw_pos_s;
+  const uint32_t tw_own = tw_pos != 0xffffffffu ? saved_pe[(tw_pos + kEndNoMatch - g.halo) / g.block_size] : 0;
 
   const uint32_t lane = threadIdx.x & 31;
   uint32_t state = kIdle;
@@ -261,8 +272,10 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
   uint32_t idle = 0xffffffffu;
   for (;;)
   {
-    // ---- refill idle lanes with the next positions of the tile
-    if (idle)
+    // ---- refill idle lanes with the next positions of the tile (a few tries: positions without an exact
+    // predecessor are not searched, smallz4.h:712-717, and must not cost their lane a whole round)
+#pragma unroll 1
+    for (uint32_t tries = 0; tries < 4 && idle; tries++)
     {
       uint32_t base = 0;
       const int leader = __ffs((int)idle) - 1;
@@ -270,20 +283,12 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
       base = __shfl_sync(0xffffffffu, base, leader);
       if (state == kIdle && !exhausted)
       {
-        // The tile is handed out in three passes, longest expected chains first: a near previous
-        // occurrence means a frequent 4-gram, i.e. a long chain (about 65536 / distance members).
-        const uint32_t vidx = base + (uint32_t)__popc(idle & ((1u << lane) - 1));
-        const uint32_t span = t1 - t0;
-        if (vidx >= 3 * span) exhausted = true;
+        p = base + (uint32_t)__popc(idle & ((1u << lane) - 1));
+        if (p >= t1) exhausted = true;
         else
         {
-          const uint32_t pass = vidx >= 2 * span ? 2 : (vidx >= span ? 1 : 0);
-          p = t0 + vidx - pass * span;
-          // smallz4.h:712-717: only positions with an exact predecessor are searched
-          uint32_t own = is_twice_inserted(g, p) ? saved_pe[(p + kEndNoMatch - g.halo) / g.block_size]
-                                                 : lds_u16(v.s_pe + 2 * (p - v.clo));
-          const uint32_t cls = own < 48 ? 0 : (own < 1024 ? 1 : 2);
-          if (own != 0 && cls == pass)
+          const uint32_t own = p == tw_pos ? tw_own : lds_u16(v.s_pe + 2 * (p - v.clo));
+          if (own != 0)
           {
             state = kWalk; len = 1; dist = 0; total = 0; budget = g.max_chain; tail = 0; ones = 0;
             hop = v.chain(p);                                        // smallz4.h:190 (absolute slot)
@@ -295,49 +300,47 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
           }
         }
       }
-      if (!__any_sync(0xffffffffu, state != kIdle))
-      {
-        // nobody is walking a chain: done when the tile has no positions left for this warp
-        idle = __ballot_sync(0xffffffffu, !exhausted);
-        if (idle == 0) break;
-        continue;
-      }
+      idle = __ballot_sync(0xffffffffu, state == kIdle && !exhausted);
+    }
+    if (!__any_sync(0xffffffffu, state != kIdle))
+    {
+      // nobody is walking a chain: done when the tile has no positions left for this warp
+      if (idle == 0) break;
+      continue;
     }
 
-    // ---- fast hops (smallz4.h:192-233, the rejecting path): follow the chain while the byte a longer match
-    // would need first differs.  A lane that meets anything else parks in a state for the slow part.
+    // ---- fast hops (smallz4.h:192-233, the rejecting path): follow the chain while the bytes a longer match
+    // would need first differ.  A lane that meets anything else parks in a state for the slow part.
+    // Written without branches around the loads: every lane executes the same dozen instructions.
 #pragma unroll 1
     for (uint32_t it = 0; it < kFastHops; it++)
     {
-      if (state == kWalk)
+      const bool walking = state == kWalk;
+      const uint32_t tot2 = total + hop;
+      const bool ends = hop == 0 || tot2 > kWindow;                  // smallz4.h:192,196
+      const bool go = walking && !ends;
+      // chain entry of the candidate q = p - tot2 (at 65535 its value ends the walk either way)
+      const uint32_t hop2 = go ? lds_u16(cbase - 2 * tot2) : 0;
+      // the candidate's bytes q+len-3 .. q+len against p's: the group the reference compares first
+      // (unaligned 32-bit read from shared memory: two aligned words and a funnel shift)
+      const smem_addr a = dl - tot2;
+      const uint32_t sh = (uint32_t)(a - v.s_data) & 3u;
+      const smem_addr w = a - sh;
+      const bool peek = go && fast;
+      const uint32_t w0 = peek ? lds_u32(w) : 0, w1 = peek ? lds_u32(w + 4) : 0;
+      const bool same = __funnelshift_r(w0, w1, sh * 8) == tail;
+      const uint32_t ones2 = hop2 == 1 ? ones + 1 : 0;
+      // a series of 1-hops is a run of one byte: the stretch is done in closed form (walk_stretch),
+      // except that short stretches are cheaper to walk while the in-smem filter applies
+      const bool stretch = run != 0 && ones2 >= (fast ? (uint32_t)kStretchMin : 1u);
+      uint32_t next_state = kWalk;
+      if (!fast || same) next_state = kCheck;                        // worth a closer look
+      if (stretch) next_state = kStretch;
+      if (ends) next_state = kFinish;
+      if (walking)
       {
-        if (hop == 0) state = kFinish;
-        else
-        {
-          total += hop;
-          if (total > kWindow) state = kFinish;
-          else
-          {
-            // chain entry of the candidate q = p - total (at total == 65535 its value ends the walk either way)
-            hop = lds_u16(cbase - 2 * total);
-            // a series of 1-hops is a run of one byte: the stretch is done in closed form (walk_stretch),
-            // except that short stretches are cheaper to walk while the in-smem filter applies
-            ones = (hop == 1) ? ones + 1 : 0;
-            if (run != 0 && ones >= (fast ? (uint32_t)kStretchMin : 1u)) state = kStretch;
-            else if (!fast) state = kCheck;
-            else
-            {
-              // the candidate's bytes q+len-3 .. q+len against p's: top byte first, then the whole group
-              const smem_addr a = dl - total;
-              if (lds_u8(a + 3) == (tail >> 24))
-              {
-                const uint32_t sh = (uint32_t)(a - v.s_data) & 3u;
-                const smem_addr w = a - sh;
-                if (__funnelshift_r(lds_u32(w), lds_u32(w + 4), sh * 8) == tail) state = kCheck;
-              }
-            }
-          }
-        }
+        state = next_state;
+        if (go) { total = tot2; hop = hop2; ones = ones2; }
       }
     }
 
