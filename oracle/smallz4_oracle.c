@@ -68,6 +68,7 @@ static cand longest_match(const octx* c, uint64_t pos, uint64_t stop)
     if (back > kWindow)
       break;
     hop = c->ring_exact[(pos - (uint64_t)back) & 0xFFFF];
+    if (c->st) c->st->chain_hops++;
 
     const uint8_t* need = cur + best.len + 1;            /* first byte a longer match must cover */
     if (need > lim)
@@ -186,7 +187,10 @@ static void find_matches(octx* c, uint64_t blk, uint64_t end, uint64_t floor_pos
       peek = 0;
     }
 
+    if (c->st) c->st->searches++;
+    { uint64_t h0 = c->st ? c->st->chain_hops : 0;
     m[i] = longest_match(c, pos, end - kEndLiterals);
+    if (c->st && c->tr && c->tr->hops) c->tr->hops[pos] = (uint32_t)(c->st->chain_hops - h0); }
 
     if ((lazy || greedy) && m[i].len != 1)
     {

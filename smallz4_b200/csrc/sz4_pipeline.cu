@@ -236,7 +236,7 @@ static int run_batch(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
              tiles_per_block, g, ctx->stage_bulk);
       PHASE(3);
       if (g.max_chain <= kLazyMax)
-        LAUNCH(ctx, k_greedy_filter, div_up(g.n_blocks, 32), 32, 0, (const uint8_t*)data, (const uint16_t*)pe, (const uint32_t*)saved_pe, mlen, mdist, g);
+        LAUNCH(ctx, k_greedy_filter, g.n_blocks, 32, 0, (const uint8_t*)data, (const uint16_t*)pe, (const uint32_t*)saved_pe, mlen, mdist, g);
       else
       {
         CK(cudaMemsetAsync(ctx->nseeds.p, 0, 4, ctx->stream));

@@ -443,52 +443,82 @@ k_seed_fix(uint32_t* mlen, uint16_t* mdist, const Seed* seeds, const uint32_t* n
 // per block) replays the reference's skipMatches / lazyEvaluation state machine and the long-run
 // shortcut, and clears the matches the reference would not have looked for.
 // ---------------------------------------------------------------------------------------------
-__global__ void k_greedy_filter(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, uint32_t* mlen,
-                                uint16_t* mdist, Geom g)
+__global__ void __launch_bounds__(32)
+k_greedy_filter(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, uint32_t* mlen, uint16_t* mdist, Geom g)
 {
-  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  (void)data;
+  const uint32_t j = blockIdx.x;
   if (j >= g.n_blocks) return;
   const uint32_t b = block_begin(g, j), s_end = search_end(g, j);
-  uint32_t skip = 0;
-  bool peek = false;
-  uint32_t prev_len = 0, prev_dist = 0;        // matches[i-1]
-  uint32_t seed = 0;                           // last inserted position in front of a skipped stretch
-  bool prev_skipped = false;
-  for (uint32_t p = b; p < s_end; p++)
+  const uint32_t lane = threadIdx.x;
+  const uint32_t tw_pos = block_end(g, j) - kEndNoMatch;         // the only position whose own entry is in saved_pe
+  const bool tw = block_len(g, j) >= kEndNoMatch && is_twice_inserted(g, tw_pos);
+  const uint32_t tw_own = tw ? saved_pe[(tw_pos + kEndNoMatch - g.halo) / g.block_size] : 0;
+
+  uint32_t skip = 0;            // skipMatches
+  bool peek = false;            // lazyEvaluation
+  uint32_t seed = 0xffffffffu;  // last position in front of a stretch the long-run shortcut skipped
+  uint32_t at = b;              // next position to look at
+  // the reference walks position by position; here a window of 32 positions is loaded at once and the
+  // state machine advances from event to event (a searched position, or a batch of skipped ones)
+  while (at < s_end)
   {
-    if (p > b && data[p] == data[p - 1] && prev_dist == 1 && prev_len > kSameLetter)
+    const uint32_t w = b + ((at - b) & ~31u);
+    const uint32_t p = w + lane;
+    uint32_t own = 0, fl = 0, fd = 0;
+    if (p < s_end)
     {
-      if (!prev_skipped) seed = p - 1;
-      prev_len -= 1;
-      mlen[p] = prev_len; mdist[p] = 1;
-      prev_skipped = true;
-      continue;
+      own = (tw && p == tw_pos) ? tw_own : pe[p];
+      fl = mlen[p]; fd = mdist[p];
     }
-    uint32_t own = is_twice_inserted(g, p) ? saved_pe[(p + kEndNoMatch - g.halo) / g.block_size] : pe[p];
-    uint32_t found_len = mlen[p], found_dist = mdist[p];
-    if (prev_skipped && g.shift == 0)
+    if (seed != 0xffffffffu && p == at && g.shift == 0 && p < s_end)
     {
-      // predecessor of p in every chain is the seed (the stretch in between was never inserted)
-      uint32_t gap = p - seed;
-      if (gap > kWindow) own = 0;
-      else if (found_dist == 1) found_dist = gap;
+      // first position behind a skipped stretch: its predecessor in every chain is the seed
+      const uint32_t gap = p - seed;
+      if (gap > kWindow) { own = 0; mlen[p] = 0; mdist[p] = 0; }
+      else if (fd == 1) { fd = gap; mdist[p] = (uint16_t)gap; }
     }
-    prev_skipped = false;
-    prev_len = 0; prev_dist = 0;
-    if (own == 0) { mlen[p] = 0; mdist[p] = 0; continue; }
-    if (skip > 0)
+    seed = 0xffffffffu;
+    const uint32_t eligible = __ballot_sync(0xffffffffu, own != 0);
+    uint32_t o = at - w;
+    bool jumped = false;
+    while (o < 32)
     {
-      skip--;
-      if (!peek) { mlen[p] = 0; mdist[p] = 0; continue; }
-      peek = false;
+      const uint32_t rem = eligible & (0xffffffffu << o);
+      if (rem == 0) break;
+      if (skip > 0 && !peek)
+      {
+        // smallz4.h:727-731: the next `skip` eligible positions are not searched
+        const uint32_t c = (uint32_t)__popc(rem), t = min(c, skip);
+        const uint32_t rank = (uint32_t)__popc(rem & ((2u << lane) - 1));      // 1-based among the remaining eligible lanes
+        const bool mine = ((rem >> lane) & 1u) && rank <= t;
+        if (mine) { mlen[p] = 0; mdist[p] = 0; }
+        skip -= t;
+        if (t == c) break;
+        const uint32_t last = __ballot_sync(0xffffffffu, mine && rank == t);
+        o = (uint32_t)__ffs((int)last);                                        // lane of the t-th one, plus one
+        continue;
+      }
+      // a searched position: the first remaining eligible one
+      const int l = __ffs((int)rem) - 1;
+      if (skip > 0) { skip--; peek = false; }                                   // the lazy peek
+      const uint32_t L = __shfl_sync(0xffffffffu, fl, l);
+      const uint32_t D = __shfl_sync(0xffffffffu, fd, l);
+      if (L != 1) { peek = (skip == 0); skip = L; }                            // smallz4.h:739-743
+      o = (uint32_t)l + 1;
+      if (D == 1 && L > kSameLetter)
+      {
+        // smallz4.h:632-643: the following positions copy {length-1, 1} and are not inserted
+        const uint32_t s = w + (uint32_t)l, count = L - kSameLetter;
+        for (uint32_t k = 1 + lane; k <= count; k += 32) { mlen[s + k] = L - k; mdist[s + k] = 1; }
+        seed = s;
+        at = s + count + 1;
+        jumped = true;
+        break;
+      }
     }
-    mlen[p] = found_len; mdist[p] = (uint16_t)found_dist;
-    prev_len = found_len; prev_dist = found_dist;
-    if (found_len != 1)
-    {
-      peek = (skip == 0);
-      skip = found_len;
-    }
+    if (!jumped) at = w + 32;
+    __syncwarp();
   }
 }
 

@@ -18,12 +18,13 @@ class Opts(ctypes.Structure):
 
 class Stats(ctypes.Structure):
     _fields_ = [("blocks", ctypes.c_uint64), ("raw_blocks", ctypes.c_uint64),
-                ("oob_first_reads", ctypes.c_uint64), ("selfmatch_skips", ctypes.c_uint64)]
+                ("oob_first_reads", ctypes.c_uint64), ("selfmatch_skips", ctypes.c_uint64),
+                ("chain_hops", ctypes.c_uint64), ("searches", ctypes.c_uint64)]
 
 
 class Trace(ctypes.Structure):
     _fields_ = [("prev_exact", ctypes.c_void_p), ("len_found", ctypes.c_void_p), ("dist_found", ctypes.c_void_p),
-                ("len_final", ctypes.c_void_p), ("cost", ctypes.c_void_p), ("skipped", ctypes.c_void_p)]
+                ("len_final", ctypes.c_void_p), ("cost", ctypes.c_void_p), ("skipped", ctypes.c_void_p), ("hops", ctypes.c_void_p)]
 
 
 def build_oracle():
@@ -91,8 +92,8 @@ def oracle_compress(data, level=9, legacy=False, dictionary=None, block_size=0, 
         total = src.size + (65535 if d is not None else 0)
         arrays = {"prev_exact": np.zeros(total, np.uint16), "len_found": np.zeros(total, np.uint32),
                   "dist_found": np.zeros(total, np.uint16), "len_final": np.zeros(total, np.uint32),
-                  "cost": np.zeros(total, np.uint32), "skipped": np.zeros(total, np.uint8)}
-        tr = Trace(*[arrays[k].ctypes.data for k in ("prev_exact", "len_found", "dist_found", "len_final", "cost", "skipped")])
+                  "cost": np.zeros(total, np.uint32), "skipped": np.zeros(total, np.uint8), "hops": np.zeros(total, np.uint32)}
+        tr = Trace(*[arrays[k].ctypes.data for k in ("prev_exact", "len_found", "dist_found", "len_final", "cost", "skipped", "hops")])
     n = oracle().sz4o_compress(src.ctypes.data if src.size else None, src.size, ctypes.byref(o), dst.ctypes.data, cap,
                                ctypes.byref(st), ctypes.byref(tr) if tr is not None else None)
     assert n >= 0, "oracle compress failed"
