@@ -216,7 +216,8 @@ enum : uint32_t { kFastHops = 8, kStretchMin = 8 };
 
 __global__ void __launch_bounds__(kSearchThreads, 1)
 k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, const uint32_t* run_fwd,
-         const uint16_t* ones_back, uint32_t* mlen, uint16_t* mdist, uint32_t tiles_per_block, Geom g, int use_bulk)
+         const uint16_t* ones_back, uint32_t* mlen, uint16_t* mdist, uint32_t tiles_per_block, Geom g, int use_bulk,
+         uint32_t fast_hops)
 {
   SZ4_DYN_SMEM(smem);
   __shared__ uint64_t bar;
@@ -296,7 +297,29 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
             if (g.shift == 0) { hop = own; run = run_fwd[p]; if (run < kMinMatch) run = 0; }
             cbase = v.s_pe + 2 * (p - v.shift - v.clo);
             dl = v.s_data + (p + len - v.dlo);
-            fast = false;                                            // the first candidate is taken unseen
+            fast = false;
+            // The first candidate is accepted unseen (smallz4.h:224-233 compare nothing while the best
+            // length is 1), so it is handled right here instead of costing the lane a round -- unless
+            // it opens a stretch of a run, which walk_stretch does without touching the bytes.
+            if (hop != 0)
+            {
+              const uint32_t nh = v.chain(p - hop);
+              if (!(run != 0 && nh == 1))
+              {
+                total = hop; hop = nh;
+                (void)try_candidate(v, p, p - total, stop, len, tail);
+                dist = total;
+                ones = nh == 1 ? 1u : 0u;
+                dl = v.s_data + (p + len - 3 - v.dlo);
+                fast = len >= 4 && p + len + 1 <= v.dhi;
+                if (--budget == 0 || p + len + 1 > stop)
+                {
+                  mlen[p] = len;
+                  mdist[p] = (uint16_t)dist;
+                  state = kIdle;
+                }
+              }
+            }
           }
         }
       }
@@ -313,7 +336,7 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
     // would need first differ.  A lane that meets anything else parks in a state for the slow part.
     // Written without branches around the loads: every lane executes the same dozen instructions.
 #pragma unroll 1
-    for (uint32_t it = 0; it < kFastHops; it++)
+    for (uint32_t it = 0; it < fast_hops; it++)
     {
       const bool walking = state == kWalk;
       const uint32_t tot2 = total + hop;
