@@ -21,7 +21,7 @@ namespace sz4
 {
 // sorted[r] = (hash << 32) | position, ascending hash then position.
 __global__ void __launch_bounds__(256)
-k_link(const uint64_t* sorted, uint32_t n, uint16_t* ph, uint32_t* rank, Geom g)
+k_link(const uint64_t* sorted, uint32_t n, uint16_t* ph, Geom g)
 {
   uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
@@ -40,7 +40,6 @@ k_link(const uint64_t* sorted, uint32_t n, uint16_t* ph, uint32_t* rank, Geom g)
     }
   }
   ph[p] = (uint16_t)d;
-  rank[p] = r;                 // where p sits in the sorted array (k_search continues long chains from there)
 }
 
 // one thread per block border k: position halo + k*block_size - 12

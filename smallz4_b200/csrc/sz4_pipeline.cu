@@ -54,11 +54,10 @@ struct sz4_ctx
   int      debug_keep = 0;
   int      force_scalar = 0;
   uint32_t fast_hops = 8;
-  uint32_t long_after = kLongAfter;   // 0: never hand a chain to the whole warp
   // device memory (grow-only)
   DevBuf data, ph, pe, mlen, mdist, scratch, hist, hist_scanned, partials, seqs, seq_count, packed,
          saved_ph, saved_pe, seeds, nseeds, seg, block_out, seg_total, dbg_len, dbg_dist, scalar_state,
-         run_fwd, ones_back, flag_last, flag_carry, mfin, dp_tasks, dp_count, dp_states, dp_overlays, dp_redo, dp_reach, seqs_tmp, path_segs, rank;
+         run_fwd, ones_back, flag_last, flag_carry, mfin, dp_tasks, dp_count, dp_states, dp_overlays, dp_redo, dp_reach, seqs_tmp, path_segs;
   unsigned long long* h_seg_total = nullptr;    // pinned: [0] segment bytes, [1] DP segments priced twice
   unsigned long long dp_redos = 0, path_redos = 0;
   bool               dp_ran = false;
@@ -201,8 +200,7 @@ static int run_batch(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
         dst = (dst == bufA) ? bufB : bufA;
       }
       PHASE(1);
-      RSV(rank, ((size_t)N + 64) * 4);
-      LAUNCH(ctx, k_link, div_up(count, 256), 256, 0, (const uint64_t*)src, count, ph, (uint32_t*)ctx->rank.p, g);
+      LAUNCH(ctx, k_link, div_up(count, 256), 256, 0, (const uint64_t*)src, count, ph, g);
       LAUNCH(ctx, k_twice_save, div_up(g.n_blocks, 64), 64, 0, ph, saved_ph, g);
       LAUNCH(ctx, k_exact_walk, div_up(count, 256), 256, 0, (const uint8_t*)data, (const uint16_t*)ph, (const uint32_t*)saved_ph, pe, first, count, g);
       LAUNCH(ctx, k_twice_save, div_up(g.n_blocks, 64), 64, 0, pe, saved_pe, g);
@@ -235,9 +233,8 @@ static int run_batch(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
         ctx->attr_set = true;
       }
       LAUNCH(ctx, k_search, g.n_blocks * tiles_per_block, kSearchThreads, kSearchSmem, (const uint8_t*)data, (const uint16_t*)pe,
-             (const uint32_t*)saved_pe, (const uint32_t*)ctx->run_fwd.p, (const uint16_t*)ctx->ones_back.p,
-             (const uint64_t*)(ctx->long_after ? src : nullptr), (const uint32_t*)ctx->rank.p, mlen, mdist,
-             tiles_per_block, g, ctx->stage_bulk, ctx->fast_hops, ctx->long_after);
+             (const uint32_t*)saved_pe, (const uint32_t*)ctx->run_fwd.p, (const uint16_t*)ctx->ones_back.p, mlen, mdist,
+             tiles_per_block, g, ctx->stage_bulk, ctx->fast_hops);
       PHASE(3);
       if (g.max_chain <= kLazyMax)
         LAUNCH(ctx, k_greedy_filter, g.n_blocks, 32, 0, (const uint8_t*)data, (const uint16_t*)pe, (const uint32_t*)saved_pe, mlen, mdist, g);
@@ -518,7 +515,7 @@ void sz4_destroy(sz4_ctx* ctx)
                     &ctx->nseeds, &ctx->seg, &ctx->block_out, &ctx->seg_total, &ctx->dbg_len, &ctx->dbg_dist, &ctx->scalar_state,
                     &ctx->run_fwd, &ctx->ones_back, &ctx->flag_last, &ctx->flag_carry, &ctx->mfin, &ctx->dp_tasks,
                     &ctx->dp_count, &ctx->dp_states, &ctx->dp_overlays, &ctx->dp_redo, &ctx->dp_reach, &ctx->seqs_tmp,
-                    &ctx->path_segs, &ctx->rank };
+                    &ctx->path_segs };
   for (DevBuf* b : all) if (b->p) cudaFree(b->p);
   if (ctx->h_seg_total) cudaFreeHost(ctx->h_seg_total);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -537,7 +534,6 @@ int sz4_set_option(sz4_ctx* ctx, const char* name, long long value)
   if (!strcmp(name, "block_size")) { ctx->block_size_override = (uint32_t)value; return SZ4_OK; }
   if (!strcmp(name, "stage_bulk")) { ctx->stage_bulk = value != 0; return SZ4_OK; }
   if (!strcmp(name, "debug_keep")) { ctx->debug_keep = value != 0; return SZ4_OK; }
-  if (!strcmp(name, "long_after")) { ctx->long_after = (uint32_t)value; return SZ4_OK; }
   if (!strcmp(name, "fast_hops")) { if (value < 1 || value > 64) return SZ4_ERR_ARG; ctx->fast_hops = (uint32_t)value; return SZ4_OK; }
   if (!strcmp(name, "profile")) { ctx->profile = value != 0; return SZ4_OK; }
   if (!strcmp(name, "force_scalar")) { ctx->force_scalar = value != 0; return SZ4_OK; }

@@ -210,72 +210,14 @@ __device__ __forceinline__ bool walk_stretch(const SearchView& v, const uint32_t
   return p + len + 1 > stop;
 }
 
-// Cooperative continuation of a long chain (all 32 lanes, uniform arguments).  The exact chain of p is the
-// list of earlier positions with p's four bytes, newest first; phase 1 left all positions sorted by
-// (hash20, position), so the chain members are found among the entries in front of a member's own
-// entry, in order and contiguous in memory: 32 candidates are tested per step instead of one per hop.
-//   - entries with another hash, or further than 65535 back, end the walk           (smallz4.h:196)
-//   - entries with p's hash but other bytes are not members (the exact chain skips them, smallz4.h:681-709)
-//   - a member whose own chain entry is 0 is the last one                           (smallz4.h:192)
-// Candidates that pass the first-group filter are then examined one at a time, in order, exactly
-// like try_candidate does for a single lane, so the result and the improvement count are the reference's.
-__device__ __forceinline__ void coop_walk(const SearchView& v, const uint64_t* sorted, const uint32_t* rank, uint32_t p,
-                                          uint32_t stop, uint32_t total, uint32_t& len, uint32_t& tail, uint32_t& dist,
-                                          uint32_t& budget)
-{
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t four_p = v.word_at(p);
-  const uint32_t h = hash20(four_p);
-  int64_t r = (int64_t)rank[p - total];                   // sorted index of the candidate the lane stopped at
-  for (;;)
-  {
-    const int64_t idx = r - 1 - (int64_t)lane;
-    const uint64_t e = idx >= 0 ? sorted[idx] : ~0ull;
-    const uint32_t q = (uint32_t)e;
-    const bool in_range = idx >= 0 && (uint32_t)(e >> 32) == h && p - q <= kWindow;
-    const bool member = in_range && v.word_at(q) == four_p;
-    const bool last = member && v.chain(q) == 0;
-    const uint32_t out_mask = __ballot_sync(0xffffffffu, !in_range);
-    const uint32_t last_mask = __ballot_sync(0xffffffffu, last);
-    uint32_t limit = out_mask ? (uint32_t)__ffs((int)out_mask) - 1 : 32;       // lanes below it are in range
-    bool ended = out_mask != 0;
-    if (last_mask)
-    {
-      const uint32_t l = (uint32_t)__ffs((int)last_mask) - 1;
-      if (l < limit) { limit = l + 1; ended = true; }
-    }
-    const bool mine = member && lane < limit;
-    uint32_t pm = __ballot_sync(0xffffffffu, mine && v.word_at(q + len - 3) == tail);
-    while (pm)
-    {
-      const uint32_t l = (uint32_t)__ffs((int)pm) - 1;
-      pm &= pm - 1;
-      uint32_t nl = len, nt = tail, better = 0;
-      if (lane == l) better = try_candidate(v, p, q, stop, nl, nt) ? 1u : 0u;
-      better = __shfl_sync(0xffffffffu, better, (int)l);
-      if (better)
-      {
-        len = __shfl_sync(0xffffffffu, nl, (int)l);
-        tail = __shfl_sync(0xffffffffu, nt, (int)l);
-        dist = p - __shfl_sync(0xffffffffu, q, (int)l);
-        if (--budget == 0 || p + len + 1 > stop) return;
-        pm = __ballot_sync(0xffffffffu, mine && lane > l && v.word_at(q + len - 3) == tail);
-      }
-    }
-    if (ended) return;
-    r -= 32;
-    if (r <= 0) return;
-  }
-}
-
 // lane states of the walk
-enum : uint32_t { kIdle = 0, kWalk = 1, kCheck = 2, kStretch = 3, kFinish = 4, kLong = 5 };
-enum : uint32_t { kFastHops = 8, kStretchMin = 8, kLongAfter = 48 };
+enum : uint32_t { kIdle = 0, kWalk = 1, kCheck = 2, kStretch = 3, kFinish = 4 };
+enum : uint32_t { kFastHops = 8, kStretchMin = 8 };
 
 __global__ void __launch_bounds__(kSearchThreads, 1)
 k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, const uint32_t* run_fwd,
-         const uint16_t* ones_back, const uint64_t* sorted, const uint32_t* rank, uint32_t* mlen, uint16_t* mdist,
-         uint32_t tiles_per_block, Geom g, int use_bulk, uint32_t fast_hops, uint32_t long_after)
+         const uint16_t* ones_back, uint32_t* mlen, uint16_t* mdist, uint32_t tiles_per_block, Geom g, int use_bulk,
+         uint32_t fast_hops)
 {
   SZ4_DYN_SMEM(smem);
   __shared__ uint64_t bar;
@@ -326,8 +268,6 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
   smem_addr cbase = v.s_pe, dl = v.s_data;   // &chain(p), &data[p + len - 3] in shared memory
   bool fast = false;                   // p + len is inside the staged bytes: candidates' bytes are too
   uint32_t ones = 0;                   // consecutive chain entries equal to 1 seen so far
-  uint32_t nhops = 0;                  // candidates visited so far for this position
-  const bool may_coop = g.shift == 0 && sorted != nullptr;
 
   // One ballot per iteration keeps `idle` (lanes that want a new position) current for all lanes.
   uint32_t idle = 0xffffffffu;
@@ -351,7 +291,7 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
           const uint32_t own = p == tw_pos ? tw_own : lds_u16(v.s_pe + 2 * (p - v.clo));
           if (own != 0)
           {
-            state = kWalk; len = 1; dist = 0; total = 0; budget = g.max_chain; tail = 0; ones = 0; nhops = 0;
+            state = kWalk; len = 1; dist = 0; total = 0; budget = g.max_chain; tail = 0; ones = 0;
             hop = v.chain(p);                                        // smallz4.h:190 (absolute slot)
             run = 0;
             if (g.shift == 0) { hop = own; run = run_fwd[p]; if (run < kMinMatch) run = 0; }
@@ -422,37 +362,13 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
       if (ends) next_state = kFinish;
       if (walking)
       {
-        // a chain that is still going after long_after candidates is finished by the whole warp (coop_walk);
-        // runs of one byte stay with the closed form of walk_stretch
-        if (may_coop && run == 0 && nhops >= long_after && !ends && len >= 4) state = kLong;
-        else
-        {
-          state = next_state;
-          if (go) { total = tot2; hop = hop2; ones = ones2; nhops++; }
-        }
-      }
-    }
-
-    // ---- long chains: one at a time, all lanes together
-    uint32_t long_mask = __ballot_sync(0xffffffffu, state == kLong);
-    while (long_mask)
-    {
-      const int l = __ffs((int)long_mask) - 1;
-      long_mask &= long_mask - 1;
-      const uint32_t cp = __shfl_sync(0xffffffffu, p, l), ctotal = __shfl_sync(0xffffffffu, total, l);
-      uint32_t clen = __shfl_sync(0xffffffffu, len, l), ctail = __shfl_sync(0xffffffffu, tail, l);
-      uint32_t cdist = __shfl_sync(0xffffffffu, dist, l), cbudget = __shfl_sync(0xffffffffu, budget, l);
-      coop_walk(v, sorted, rank, cp, stop, ctotal, clen, ctail, cdist, cbudget);
-      if (lane == (uint32_t)l)
-      {
-        mlen[cp] = clen;
-        mdist[cp] = (uint16_t)cdist;
-        state = kIdle;
+        state = next_state;
+        if (go) { total = tot2; hop = hop2; ones = ones2; }
       }
     }
 
     // ---- slow part: candidates that passed the first byte, stretches, finished walks
-    if (state >= kCheck && state != kLong)
+    if (state >= kCheck)
     {
       bool finish = state == kFinish;
       if (!finish)
