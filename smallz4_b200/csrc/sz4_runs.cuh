@@ -48,16 +48,27 @@ __global__ void __launch_bounds__(kFlagThreads) k_flag_reduce(F f, uint32_t* chu
   if (threadIdx.x == 0) chunk_last[blockIdx.x] = best ? best - 1 : SZ4_NOFLAG;
 }
 
-// single CTA: chunk_carry[c] = last flagged index before chunk c
-__global__ void k_flag_carry(const uint32_t* chunk_last, uint32_t* chunk_carry, uint32_t chunks)
+// one warp: chunk_carry[c] = last flagged index before chunk c (exclusive max-scan, 32 chunks per step)
+__global__ void __launch_bounds__(32) k_flag_carry(const uint32_t* chunk_last, uint32_t* chunk_carry, uint32_t chunks)
 {
-  if (blockIdx.x != 0 || threadIdx.x != 0) return;
-  uint32_t run = SZ4_NOFLAG;
-  for (uint32_t c = 0; c < chunks; c++)
+  if (blockIdx.x != 0) return;
+  const uint32_t lane = threadIdx.x;
+  uint32_t run = 0;                                    // index + 1 of the last flag so far, 0 = none
+  for (uint32_t c0 = 0; c0 < chunks; c0 += 32)
   {
-    chunk_carry[c] = run;
-    uint32_t v = chunk_last[c];
-    if (v != SZ4_NOFLAG) run = v;
+    const uint32_t c = c0 + lane;
+    const uint32_t v = c < chunks ? chunk_last[c] : SZ4_NOFLAG;
+    uint32_t incl = v == SZ4_NOFLAG ? 0 : v + 1;       // flags only move right: a later one is larger
+#pragma unroll
+    for (uint32_t d = 1; d < 32; d <<= 1)
+    {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl = max(incl, t);
+    }
+    uint32_t before = __shfl_up_sync(0xffffffffu, incl, 1);
+    before = lane == 0 ? run : max(before, run);
+    if (c < chunks) chunk_carry[c] = before ? before - 1 : SZ4_NOFLAG;
+    run = max(run, __shfl_sync(0xffffffffu, incl, 31));
   }
 }
 
