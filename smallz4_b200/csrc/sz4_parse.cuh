@@ -207,7 +207,7 @@ __device__ __forceinline__ void dp_segment(const uint32_t* mlen, const uint16_t*
                                            uint32_t b, uint32_t n, uint32_t lo, uint32_t hi, bool resume, uint32_t ub_resume,
                                            unsigned char* smem, uint32_t& ub_hi, uint32_t& ub_lo)
 {
-  const uint32_t lane = threadIdx.x;
+  const uint32_t lane = threadIdx.x & 31;
   const uint32_t start = resume ? hi : min(hi + (uint32_t)kDpWarm, n);
   const bool true_end = (start == n) && !resume;
   // a cold start prices the positions as if the block ended at `start` (smallz4.h:389: the last five are free,
@@ -485,13 +485,15 @@ k_dp_group_reach(const uint32_t* mlen, uint32_t* group_reach, uint32_t groups_pe
 
 // One warp per block: exclusive prefix maximum of the group reaches, 32 groups per step, and a boundary
 // wherever the segment is long enough and nothing from the left reaches more than kDpSlack beyond it.
-__global__ void __launch_bounds__(32)
+// (kernels that give one warp a sequential job pack four such warps into a CTA: a warp's scheduler is
+// its index in the CTA modulo 4, so single-warp CTAs would all queue on the first of the SM's four schedulers)
+__global__ void __launch_bounds__(128)
 k_dp_plan(const uint32_t* group_reach, uint32_t groups_per_block, DpTask* tasks, uint32_t* task_count, uint32_t max_seg, Geom g)
 {
-  const uint32_t j = blockIdx.x;
+  const uint32_t j = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (j >= g.n_blocks) return;
   const uint32_t n = block_len(g, j);
-  const uint32_t lane = threadIdx.x;
+  const uint32_t lane = threadIdx.x & 31;
   DpTask* out = tasks + (size_t)j * max_seg;
   if (n <= kEndNoMatch) { if (lane == 0) task_count[j] = 0; return; }     // smallz4.h:755
   const uint32_t* gr = group_reach + (size_t)j * groups_per_block;
@@ -542,31 +544,34 @@ __device__ __forceinline__ DpOverlay overlay_of(uint32_t* base, uint32_t task_in
   return o;
 }
 
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(128, 1)
 k_dp_spec(const uint32_t* mlen, const uint16_t* mdist, uint32_t* mfin, DpScratch s, const DpTask* tasks,
           const uint32_t* task_count, DpState* states, uint32_t* overlays, uint32_t max_seg, Geom g)
 {
   SZ4_DYN_SMEM(smem);
-  const uint32_t j = blockIdx.x / max_seg, k = blockIdx.x % max_seg;
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t ti = blockIdx.x * 4 + warp;                     // one task per warp
+  const uint32_t j = ti / max_seg, k = ti % max_seg;
   if (j >= g.n_blocks || k >= task_count[j]) return;
-  const DpTask t = tasks[blockIdx.x];
+  const DpTask t = tasks[ti];
   uint32_t ub_hi, ub_lo;
-  dp_segment(mlen, mdist, mfin, s, overlay_of(overlays, blockIdx.x), block_begin(g, j), block_len(g, j), t.lo, t.hi,
-             false, 0, smem, ub_hi, ub_lo);
-  if (threadIdx.x == 0) { DpState st; st.ub_hi = ub_hi; st.ub_lo = ub_lo; st.redone = 0; st.cum = 0; states[blockIdx.x] = st; }
+  dp_segment(mlen, mdist, mfin, s, overlay_of(overlays, ti), block_begin(g, j), block_len(g, j), t.lo, t.hi,
+             false, 0, smem + warp * kDpSmem, ub_hi, ub_lo);
+  if ((threadIdx.x & 31) == 0) { DpState st; st.ub_hi = ub_hi; st.ub_lo = ub_lo; st.redone = 0; st.cum = 0; states[ti] = st; }
 }
 
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(128, 1)
 k_dp_verify(const uint32_t* mlen, const uint16_t* mdist, uint32_t* mfin, DpScratch s, const DpTask* tasks,
             const uint32_t* task_count, DpState* states, uint32_t* overlays, uint32_t max_seg, uint32_t* redo_count, Geom g)
 {
-  SZ4_DYN_SMEM(smem);
-  const uint32_t j = blockIdx.x;
+  SZ4_DYN_SMEM(smem_all);
+  unsigned char* smem = smem_all + (threadIdx.x >> 5) * kDpSmem;
+  const uint32_t j = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (j >= g.n_blocks) return;
   const uint32_t cnt = task_count[j];
   if (cnt < 2) return;
   const uint32_t b = block_begin(g, j), n = block_len(g, j);
-  const uint32_t lane = threadIdx.x;
+  const uint32_t lane = threadIdx.x & 31;
   uint32_t cum = 0;                                              // costs of the segment to the right minus true costs: 0 at the top
   for (int32_t k = (int32_t)cnt - 2; k >= 0; k--)
   {
@@ -659,7 +664,7 @@ enum : uint32_t { kPathSeg = SZ4_PATH_SEG, kPathWarm = SZ4_PATH_WARM };
 __device__ __forceinline__ void path_walk(const uint32_t* mlen, const uint16_t* mdist, uint32_t b, uint32_t n, uint32_t from,
                                           uint32_t lo, uint32_t hi, SeqRec* out, uint32_t& count, uint32_t& cover, uint32_t& leave)
 {
-  const uint32_t lane = threadIdx.x;
+  const uint32_t lane = threadIdx.x & 31;
   uint32_t at = from;         // current position on the path (block relative)
   count = 0; cover = 0; leave = 0;
   // the walk reads 128 positions at a time and keeps the following 256 in flight (two sets of registers,
@@ -735,11 +740,12 @@ __device__ __forceinline__ SeqRec* path_seg_records(SeqRec* tmp, uint32_t seq_st
   return tmp + (size_t)j * seq_stride + (size_t)k * (kPathSeg / min_len + 1);
 }
 
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(128)
 k_path_spec(const uint32_t* mlen, const uint16_t* mdist, SeqRec* tmp, uint32_t seq_stride, PathSeg* segs, uint32_t max_seg,
             uint32_t min_len, Geom g)
 {
-  const uint32_t j = blockIdx.x / max_seg, k = blockIdx.x % max_seg;
+  const uint32_t si = blockIdx.x * 4 + (threadIdx.x >> 5);       // one segment per warp
+  const uint32_t j = si / max_seg, k = si % max_seg;
   if (j >= g.n_blocks) return;
   const uint32_t b = block_begin(g, j), n = block_len(g, j);
   const uint32_t lo = k * kPathSeg;
@@ -748,21 +754,21 @@ k_path_spec(const uint32_t* mlen, const uint16_t* mdist, SeqRec* tmp, uint32_t s
   const uint32_t from = lo > kPathWarm ? lo - kPathWarm : 0;
   uint32_t count, cover, leave;
   path_walk(mlen, mdist, b, n, from, lo, hi, path_seg_records(tmp, seq_stride, j, k, min_len), count, cover, leave);
-  if (threadIdx.x == 0)
+  if ((threadIdx.x & 31) == 0)
   {
     PathSeg ps; ps.entry = max(lo, cover); ps.leave = max(hi, leave); ps.count = count; ps.base = 0;
-    segs[blockIdx.x] = ps;
+    segs[si] = ps;
   }
 }
 
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(128)
 k_path_join(const uint32_t* mlen, const uint16_t* mdist, SeqRec* tmp, uint32_t seq_stride, PathSeg* segs, uint32_t max_seg,
             uint32_t min_len, uint32_t* seq_count, uint32_t* redo_count, Geom g)
 {
-  const uint32_t j = blockIdx.x;
+  const uint32_t j = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (j >= g.n_blocks) return;
   const uint32_t b = block_begin(g, j), n = block_len(g, j);
-  const uint32_t lane = threadIdx.x;
+  const uint32_t lane = threadIdx.x & 31;
   const uint32_t nseg = (n + kPathSeg - 1) / kPathSeg;
   uint32_t entry = 0, base = 0;                                  // true entry into the next segment; records so far
   for (uint32_t k = 0; k < nseg; k++)

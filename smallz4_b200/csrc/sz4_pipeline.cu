@@ -237,7 +237,7 @@ static int run_batch(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
              tiles_per_block, g, ctx->stage_bulk, ctx->fast_hops);
       PHASE(3);
       if (g.max_chain <= kLazyMax)
-        LAUNCH(ctx, k_greedy_filter, g.n_blocks, 32, 0, (const uint8_t*)data, (const uint16_t*)pe, (const uint32_t*)saved_pe, mlen, mdist, g);
+        LAUNCH(ctx, k_greedy_filter, div_up(g.n_blocks, 4), 128, 0, (const uint8_t*)data, (const uint16_t*)pe, (const uint32_t*)saved_pe, mlen, mdist, g);
       else
       {
         CK(cudaMemsetAsync(ctx->nseeds.p, 0, 4, ctx->stream));
@@ -272,8 +272,8 @@ static int run_batch(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
   {
     if (!ctx->dp_attr_set)
     {
-      CK(cudaFuncSetAttribute(k_dp_spec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDpSmem));
-      CK(cudaFuncSetAttribute(k_dp_verify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDpSmem));
+      CK(cudaFuncSetAttribute(k_dp_spec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * kDpSmem)));
+      CK(cudaFuncSetAttribute(k_dp_verify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * kDpSmem)));
       ctx->dp_attr_set = true;
     }
     const uint32_t max_seg = g.block_size / kDpSeg + 2;
@@ -290,11 +290,11 @@ static int run_batch(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
     RSV(dp_reach, (size_t)g.n_blocks * groups_per_block * 4 + 64);
     LAUNCH(ctx, k_dp_group_reach, div_up((uint64_t)g.n_blocks * div_up(groups_per_block, 32) * 32, 256), 256, 0,
            (const uint32_t*)mlen, (uint32_t*)ctx->dp_reach.p, groups_per_block, g);
-    LAUNCH(ctx, k_dp_plan, g.n_blocks, 32, 0, (const uint32_t*)ctx->dp_reach.p, groups_per_block, (DpTask*)ctx->dp_tasks.p,
+    LAUNCH(ctx, k_dp_plan, div_up(g.n_blocks, 4), 128, 0, (const uint32_t*)ctx->dp_reach.p, groups_per_block, (DpTask*)ctx->dp_tasks.p,
            (uint32_t*)ctx->dp_count.p, max_seg, g);
-    LAUNCH(ctx, k_dp_spec, n_tasks, 32, kDpSmem, (const uint32_t*)mlen, (const uint16_t*)mdist, mfin, dp, (const DpTask*)ctx->dp_tasks.p,
+    LAUNCH(ctx, k_dp_spec, div_up(n_tasks, 4), 128, 4 * kDpSmem, (const uint32_t*)mlen, (const uint16_t*)mdist, mfin, dp, (const DpTask*)ctx->dp_tasks.p,
            (const uint32_t*)ctx->dp_count.p, (DpState*)ctx->dp_states.p, (uint32_t*)ctx->dp_overlays.p, max_seg, g);
-    LAUNCH(ctx, k_dp_verify, g.n_blocks, 32, kDpSmem, (const uint32_t*)mlen, (const uint16_t*)mdist, mfin, dp, (const DpTask*)ctx->dp_tasks.p,
+    LAUNCH(ctx, k_dp_verify, div_up(g.n_blocks, 4), 128, 4 * kDpSmem, (const uint32_t*)mlen, (const uint16_t*)mdist, mfin, dp, (const DpTask*)ctx->dp_tasks.p,
            (const uint32_t*)ctx->dp_count.p, (DpState*)ctx->dp_states.p, (uint32_t*)ctx->dp_overlays.p, max_seg,
            (uint32_t*)ctx->dp_redo.p, g);
     if (ctx->debug_keep)
@@ -309,9 +309,9 @@ static int run_batch(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
     const uint32_t max_pseg = g.block_size / kPathSeg + 1;
     RSV(seqs_tmp, (size_t)g.n_blocks * seq_stride * sizeof(SeqRec));
     RSV(path_segs, (size_t)g.n_blocks * max_pseg * sizeof(PathSeg) + 64);
-    LAUNCH(ctx, k_path_spec, g.n_blocks * max_pseg, 32, 0, final_len, (const uint16_t*)mdist, (SeqRec*)ctx->seqs_tmp.p, seq_stride,
+    LAUNCH(ctx, k_path_spec, div_up(g.n_blocks * max_pseg, 4), 128, 0, final_len, (const uint16_t*)mdist, (SeqRec*)ctx->seqs_tmp.p, seq_stride,
            (PathSeg*)ctx->path_segs.p, max_pseg, min_len, g);
-    LAUNCH(ctx, k_path_join, g.n_blocks, 32, 0, final_len, (const uint16_t*)mdist, (SeqRec*)ctx->seqs_tmp.p, seq_stride,
+    LAUNCH(ctx, k_path_join, div_up(g.n_blocks, 4), 128, 0, final_len, (const uint16_t*)mdist, (SeqRec*)ctx->seqs_tmp.p, seq_stride,
            (PathSeg*)ctx->path_segs.p, max_pseg, min_len, (uint32_t*)ctx->seq_count.p, (uint32_t*)ctx->dp_redo.p, g);
     LAUNCH(ctx, k_path_compact, g.n_blocks * max_pseg, 128, 0, (const SeqRec*)ctx->seqs_tmp.p, (SeqRec*)ctx->seqs.p, seq_stride,
            (const PathSeg*)ctx->path_segs.p, max_pseg, min_len, (const uint32_t*)ctx->seq_count.p, g);

@@ -466,14 +466,14 @@ k_seed_fix(uint32_t* mlen, uint16_t* mdist, const Seed* seeds, const uint32_t* n
 // per block) replays the reference's skipMatches / lazyEvaluation state machine and the long-run
 // shortcut, and clears the matches the reference would not have looked for.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(128)
 k_greedy_filter(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, uint32_t* mlen, uint16_t* mdist, Geom g)
 {
   (void)data;
-  const uint32_t j = blockIdx.x;
+  const uint32_t j = blockIdx.x * 4 + (threadIdx.x >> 5);        // one block per warp, four warps per CTA
   if (j >= g.n_blocks) return;
   const uint32_t b = block_begin(g, j), s_end = search_end(g, j);
-  const uint32_t lane = threadIdx.x;
+  const uint32_t lane = threadIdx.x & 31;
   const uint32_t tw_pos = block_end(g, j) - kEndNoMatch;         // the only position whose own entry is in saved_pe
   const bool tw = block_len(g, j) >= kEndNoMatch && is_twice_inserted(g, tw_pos);
   const uint32_t tw_own = tw ? saved_pe[(tw_pos + kEndNoMatch - g.halo) / g.block_size] : 0;
