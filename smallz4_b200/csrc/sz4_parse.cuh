@@ -381,14 +381,25 @@ __device__ __forceinline__ void dp_segment(const uint32_t* mlen, const uint16_t*
       const uint32_t wlen = (!forced && M >= kMinMatch) ? M - 3 : 0;
       uint32_t bl_f = bl | (forced ? 0x80000000u : 0u);
 
-      // ------------------------------ sequential part: 32 positions, high to low (dp_steps above)
-      if (i0 + 31 <= last_priced)
-        dp_steps<false>(lane, i0, last_priced, wlen, bc, bl_f, next_cost, until_bump, s_out);
+      if (i0 + 31 <= last_priced && __all_sync(0xffffffffu, forced))
+      {
+        // every position of the group takes its long run unpriced (smallz4.h:410-416): the costs only depend
+        // on costs >= 65299 positions ahead, nothing is sequential, and each match resets the literal counter
+        cur = bc; keep = bl;
+        next_cost = __shfl_sync(0xffffffffu, bc, 0);
+        until_bump = 15;
+      }
       else
-        dp_steps<true>(lane, i0, last_priced, wlen, bc, bl_f, next_cost, until_bump, s_out);
-      __syncwarp();
-      const uint2 mine = s_out[lane];
-      cur = mine.x; keep = mine.y;
+      {
+        // ------------------------------ sequential part: 32 positions, high to low (dp_steps above)
+        if (i0 + 31 <= last_priced)
+          dp_steps<false>(lane, i0, last_priced, wlen, bc, bl_f, next_cost, until_bump, s_out);
+        else
+          dp_steps<true>(lane, i0, last_priced, wlen, bc, bl_f, next_cost, until_bump, s_out);
+        __syncwarp();
+        const uint2 mine = s_out[lane];
+        cur = mine.x; keep = mine.y;
+      }
 
     }
 
