@@ -205,7 +205,8 @@ __device__ __forceinline__ void dp_steps(uint32_t lane, uint32_t i0, uint32_t la
 // Own-range results go to the block arrays (s) and the final lengths to mfin.
 __device__ __forceinline__ void dp_segment(const uint32_t* mlen, const uint16_t* mdist, uint32_t* mfin, DpScratch s, DpOverlay ovl,
                                            uint32_t b, uint32_t n, uint32_t lo, uint32_t hi, bool resume, uint32_t ub_resume,
-                                           unsigned char* smem, uint32_t& ub_hi, uint32_t& ub_lo)
+                                           unsigned char* smem, uint32_t& ub_hi, uint32_t& ub_lo, const uint32_t* reach_before = nullptr,
+                                           bool* stopped = nullptr)
 {
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t start = resume ? hi : min(hi + (uint32_t)kDpWarm, n);
@@ -236,6 +237,10 @@ __device__ __forceinline__ void dp_segment(const uint32_t* mlen, const uint16_t*
   uint32_t prv = 0;                                              // cost of (group+1)*32 + lane
   uint32_t p5 = 0xffffffffu, p6a = 0xffffffffu, p6b = 0xffffffffu;   // st5 of group+1, st6 of group+1 / group+2
   bool have_prev = false;                                        // a group above this one exists
+  uint32_t far_end = 0xffffffffu, far_cost = 0;                  // last end position of an unpriced long run and its cost
+  uint32_t settled = 0;                                          // resume: positions in a row that reproduce the earlier result
+  bool settled_match = false, early_stop = false;
+  uint32_t settled_diff = 0;
   ub_hi = until_bump;
   if (resume)
   {
@@ -301,7 +306,10 @@ __device__ __forceinline__ void dp_segment(const uint32_t* mlen, const uint16_t*
       if (M >= kSameLetter && D == 1)
       {
         forced = true;                                             // smallz4.h:410-416
-        bc = v.cost(i + M) + 1 + 2 + 1 + (M - 19) / 255;
+        // inside one long run every position's match ends at the same place: remember that cost
+        const uint32_t end = i + M;
+        if (end != far_end) { far_end = end; far_cost = v.cost(end); }
+        bc = far_cost + 1 + 2 + 1 + (M - 19) / 255;
         bl = M;
       }
       else if (M >= kMinMatch)
@@ -434,6 +442,28 @@ __device__ __forceinline__ void dp_segment(const uint32_t* mlen, const uint16_t*
     if (p5 != 0xffffffffu && (p5 >> 8) <= (v5 >> 8)) v6 = ((p5 >> 8) << 8) | ((p5 & 255u) - 32u);
     uint32_t v7 = v6;
     if (p6b != 0xffffffffu && (p6b >> 8) <= (v6 >> 8)) v7 = ((p6b >> 8) << 8) | ((p6b & 255u) - 64u);
+    if (resume && reach_before != nullptr && i0 + 32 <= hi)
+    {
+      // A redo may stop once it provably reproduces the earlier (speculative) pass: over a span longer than
+      // anything further left can look at, the costs differ from the earlier ones by one constant, the chosen
+      // lengths are identical, and a match was chosen in the span (which also pins the literal counter).
+      const uint32_t diff = cur - __ldcg(s.cost + b + i);
+      const uint32_t d0 = __shfl_sync(0xffffffffu, diff, 0);
+      const bool same = __all_sync(0xffffffffu, diff == d0 && keep == mfin[b + i]);
+      if (same && (settled == 0 || d0 == settled_diff))
+      {
+        settled += 32; settled_diff = d0;
+        settled_match = settled_match || __any_sync(0xffffffffu, keep != 1);
+      }
+      else { settled = 0; settled_match = false; }
+      // the span must cover everything positions further left can look at (reach_before = largest position + length left of this group)
+      if (settled_match && settled >= 256 && __ldcg(reach_before + i0 / 32) <= i0 + settled && i0 >= lo + kDpRing + 256)
+      {
+        // everything from lo up to here stays as the earlier pass left it (its costs in its own frame)
+        early_stop = true;
+        break;
+      }
+    }
     if (exists)
     {
       if (i0 >= hi)
@@ -456,7 +486,8 @@ __device__ __forceinline__ void dp_segment(const uint32_t* mlen, const uint16_t*
     have_prev = true;
     __syncwarp();
   }
-  ub_lo = until_bump;
+  if (stopped) *stopped = early_stop;
+  if (!early_stop) ub_lo = until_bump;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -499,7 +530,7 @@ k_dp_group_reach(const uint32_t* mlen, uint32_t* group_reach, uint32_t groups_pe
 // (kernels that give one warp a sequential job pack four such warps into a CTA: a warp's scheduler is
 // its index in the CTA modulo 4, so single-warp CTAs would all queue on the first of the SM's four schedulers)
 __global__ void __launch_bounds__(128)
-k_dp_plan(const uint32_t* group_reach, uint32_t groups_per_block, DpTask* tasks, uint32_t* task_count, uint32_t max_seg, Geom g)
+k_dp_plan(uint32_t* group_reach, uint32_t groups_per_block, DpTask* tasks, uint32_t* task_count, uint32_t max_seg, Geom g)
 {
   const uint32_t j = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (j >= g.n_blocks) return;
@@ -507,7 +538,7 @@ k_dp_plan(const uint32_t* group_reach, uint32_t groups_per_block, DpTask* tasks,
   const uint32_t lane = threadIdx.x & 31;
   DpTask* out = tasks + (size_t)j * max_seg;
   if (n <= kEndNoMatch) { if (lane == 0) task_count[j] = 0; return; }     // smallz4.h:755
-  const uint32_t* gr = group_reach + (size_t)j * groups_per_block;
+  uint32_t* gr = group_reach + (size_t)j * groups_per_block;   // in: reach of each group; out: reach of everything left of it
   const uint32_t groups = (n + 31) / 32;
   uint32_t count = 0, last = 0, carry = 0;
   uint32_t nxt = lane < groups ? gr[lane] : 0;
@@ -525,6 +556,7 @@ k_dp_plan(const uint32_t* group_reach, uint32_t groups_per_block, DpTask* tasks,
     }
     uint32_t before = __shfl_up_sync(0xffffffffu, incl, 1);
     before = lane == 0 ? carry : max(before, carry);
+    if (g0 + lane < groups) gr[g0 + lane] = before;
     const uint32_t x0 = (g0 + lane) * 32;
     const bool fits = g0 + lane < groups && x0 > 0 && x0 + 64 <= n && before <= x0 + kDpSlack;
     // at most a few boundaries per 1024 positions: take them in order
@@ -555,25 +587,35 @@ __device__ __forceinline__ DpOverlay overlay_of(uint32_t* base, uint32_t task_in
   return o;
 }
 
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(32)
 k_dp_spec(const uint32_t* mlen, const uint16_t* mdist, uint32_t* mfin, DpScratch s, const DpTask* tasks,
-          const uint32_t* task_count, DpState* states, uint32_t* overlays, uint32_t max_seg, Geom g)
+          const uint32_t* task_count, DpState* states, uint32_t* overlays, uint32_t max_seg, uint32_t* stats, Geom g)
 {
   SZ4_DYN_SMEM(smem);
-  const uint32_t warp = threadIdx.x >> 5;
-  const uint32_t ti = blockIdx.x * 4 + warp;                     // one task per warp
+  const uint32_t warp = 0;
+  const uint32_t ti = blockIdx.x;                                // one task per (single-warp) CTA: tasks differ a lot in length
   const uint32_t j = ti / max_seg, k = ti % max_seg;
   if (j >= g.n_blocks || k >= task_count[j]) return;
   const DpTask t = tasks[ti];
   uint32_t ub_hi, ub_lo;
+#ifndef SZ4_EMU
+  const long long t0 = clock64();
+#endif
   dp_segment(mlen, mdist, mfin, s, overlay_of(overlays, ti), block_begin(g, j), block_len(g, j), t.lo, t.hi,
              false, 0, smem + warp * kDpSmem, ub_hi, ub_lo);
-  if ((threadIdx.x & 31) == 0) { DpState st; st.ub_hi = ub_hi; st.ub_lo = ub_lo; st.redone = 0; st.cum = 0; states[ti] = st; }
+  if ((threadIdx.x & 31) == 0)
+  {
+    DpState st; st.ub_hi = ub_hi; st.ub_lo = ub_lo; st.redone = 0; st.cum = 0; states[ti] = st;
+#ifndef SZ4_EMU
+    if (stats) { const unsigned dt = (unsigned)((clock64() - t0) >> 10); atomicMax(stats + 4, dt); atomicAdd(stats + 5, dt); if (dt > 4000) atomicMax(stats + 6, t.hi - t.lo); }
+#endif
+  }
 }
 
 __global__ void __launch_bounds__(128, 1)
 k_dp_verify(const uint32_t* mlen, const uint16_t* mdist, uint32_t* mfin, DpScratch s, const DpTask* tasks,
-            const uint32_t* task_count, DpState* states, uint32_t* overlays, uint32_t max_seg, uint32_t* redo_count, Geom g)
+            const uint32_t* task_count, DpState* states, uint32_t* overlays, uint32_t max_seg, uint32_t* redo_count,
+            bool allow_early_stop, const uint32_t* reach_before, uint32_t groups_per_block, Geom g)
 {
   SZ4_DYN_SMEM(smem_all);
   unsigned char* smem = smem_all + (threadIdx.x >> 5) * kDpSmem;
@@ -584,6 +626,10 @@ k_dp_verify(const uint32_t* mlen, const uint16_t* mdist, uint32_t* mfin, DpScrat
   const uint32_t b = block_begin(g, j), n = block_len(g, j);
   const uint32_t lane = threadIdx.x & 31;
   uint32_t cum = 0;                                              // costs of the segment to the right minus true costs: 0 at the top
+#ifndef SZ4_EMU
+  const long long tv0 = clock64();
+  long long tredo = 0;
+#endif
   for (int32_t k = (int32_t)cnt - 2; k >= 0; k--)
   {
     const uint32_t idx = j * max_seg + (uint32_t)k;
@@ -607,13 +653,24 @@ k_dp_verify(const uint32_t* mlen, const uint16_t* mdist, uint32_t* mfin, DpScrat
     else
     {
       uint32_t ub_hi, ub_lo;
-      dp_segment(mlen, mdist, mfin, s, o, b, n, t.lo, t.hi, true, right.ub_lo, smem, ub_hi, ub_lo);
+#ifndef SZ4_EMU
+      const long long tr0 = clock64();
+#endif
+      bool stopped = false;
+      ub_lo = st.ub_lo;                                          // an early stop keeps the earlier pass's state at lo
+      dp_segment(mlen, mdist, mfin, s, o, b, n, t.lo, t.hi, true, right.ub_lo, smem, ub_hi, ub_lo, allow_early_stop ? reach_before + (size_t)j * groups_per_block : nullptr, &stopped);
+#ifndef SZ4_EMU
+      tredo += clock64() - tr0;
+#endif
       st.ub_lo = ub_lo; st.redone = 1; st.cum = cum;
       if (lane == 0) atomicAdd(redo_count, 1u);
     }
     if (lane == 0) states[idx] = st;
     __syncwarp();
   }
+#ifndef SZ4_EMU
+  if (lane == 0) { atomicMax(redo_count + 8, (unsigned)((clock64() - tv0) >> 10)); atomicMax(redo_count + 9, (unsigned)(tredo >> 10)); }
+#endif
 }
 
 // debug only: bring every segment's costs into the true frame (they differ by a constant per segment)

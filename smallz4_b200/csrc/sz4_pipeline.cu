@@ -267,12 +267,12 @@ static int run_batch(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
   const uint32_t* final_len = mlen;
   ctx->dp_ran = false;
   RSV(dp_redo, 64);
-  CK(cudaMemsetAsync(ctx->dp_redo.p, 0, 8, ctx->stream));
+  CK(cudaMemsetAsync(ctx->dp_redo.p, 0, 64, ctx->stream));
   if (g.max_chain > kGreedyMax)                                   // smallz4.h:755
   {
     if (!ctx->dp_attr_set)
     {
-      CK(cudaFuncSetAttribute(k_dp_spec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * kDpSmem)));
+      CK(cudaFuncSetAttribute(k_dp_spec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDpSmem));
       CK(cudaFuncSetAttribute(k_dp_verify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * kDpSmem)));
       ctx->dp_attr_set = true;
     }
@@ -290,13 +290,13 @@ static int run_batch(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
     RSV(dp_reach, (size_t)g.n_blocks * groups_per_block * 4 + 64);
     LAUNCH(ctx, k_dp_group_reach, div_up((uint64_t)g.n_blocks * div_up(groups_per_block, 32) * 32, 256), 256, 0,
            (const uint32_t*)mlen, (uint32_t*)ctx->dp_reach.p, groups_per_block, g);
-    LAUNCH(ctx, k_dp_plan, div_up(g.n_blocks, 4), 128, 0, (const uint32_t*)ctx->dp_reach.p, groups_per_block, (DpTask*)ctx->dp_tasks.p,
+    LAUNCH(ctx, k_dp_plan, div_up(g.n_blocks, 4), 128, 0, (uint32_t*)ctx->dp_reach.p, groups_per_block, (DpTask*)ctx->dp_tasks.p,
            (uint32_t*)ctx->dp_count.p, max_seg, g);
-    LAUNCH(ctx, k_dp_spec, div_up(n_tasks, 4), 128, 4 * kDpSmem, (const uint32_t*)mlen, (const uint16_t*)mdist, mfin, dp, (const DpTask*)ctx->dp_tasks.p,
-           (const uint32_t*)ctx->dp_count.p, (DpState*)ctx->dp_states.p, (uint32_t*)ctx->dp_overlays.p, max_seg, g);
+    LAUNCH(ctx, k_dp_spec, n_tasks, 32, kDpSmem, (const uint32_t*)mlen, (const uint16_t*)mdist, mfin, dp, (const DpTask*)ctx->dp_tasks.p,
+           (const uint32_t*)ctx->dp_count.p, (DpState*)ctx->dp_states.p, (uint32_t*)ctx->dp_overlays.p, max_seg, (uint32_t*)ctx->dp_redo.p, g);
     LAUNCH(ctx, k_dp_verify, div_up(g.n_blocks, 4), 128, 4 * kDpSmem, (const uint32_t*)mlen, (const uint16_t*)mdist, mfin, dp, (const DpTask*)ctx->dp_tasks.p,
            (const uint32_t*)ctx->dp_count.p, (DpState*)ctx->dp_states.p, (uint32_t*)ctx->dp_overlays.p, max_seg,
-           (uint32_t*)ctx->dp_redo.p, g);
+           (uint32_t*)ctx->dp_redo.p, ctx->debug_keep == 0, (const uint32_t*)ctx->dp_reach.p, groups_per_block, g);
     if (ctx->debug_keep)
       LAUNCH(ctx, k_dp_cost_fix, n_tasks, 256, 0, dp, (const DpTask*)ctx->dp_tasks.p, (const uint32_t*)ctx->dp_count.p,
              (const DpState*)ctx->dp_states.p, max_seg, g);
@@ -327,7 +327,7 @@ static int run_batch(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
   PHASE(7);
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
   CK(cudaMemcpyAsync(ctx->h_seg_total, ctx->seg_total.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaMemcpyAsync(ctx->h_seg_total + 1, ctx->dp_redo.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->h_seg_total + 1, ctx->dp_redo.p, 48, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaGetLastError());
   float ms = 0;
@@ -657,6 +657,8 @@ int sz4_last_stats(const sz4_ctx* ctx, double* kernel_ms, unsigned long long* la
 }
 
 long long sz4_last_dp_redos(const sz4_ctx* ctx) { return ctx ? (long long)ctx->dp_redos : -1; }
+/* debug: raw counters of the last batch (k-cycles): [2] longest spec task, total spec, its length; [4] verify per block max, redo max */
+const unsigned* sz4_debug_counters(const sz4_ctx* ctx) { return ctx ? (const unsigned*)(ctx->h_seg_total + 1) : nullptr; }
 long long sz4_last_path_redos(const sz4_ctx* ctx) { return ctx ? (long long)ctx->path_redos : -1; }
 
 int sz4_last_phase_ms(const sz4_ctx* ctx, double* out7)
