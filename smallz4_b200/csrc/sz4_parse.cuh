@@ -273,6 +273,27 @@ __device__ __forceinline__ void dp_segment(const uint32_t* mlen, const uint16_t*
   // matches of the first group; later groups are prefetched one group ahead
   uint32_t Mn = 0, Dn = 0;
   { const uint32_t i = top_group * 32 + lane; if (i < start) { Mn = mlen[b + i]; Dn = mdist[b + i]; } }
+  // ... and three more groups are kept in flight behind it: a cheap group (all literals, all long runs) takes
+  // less time than a DRAM round trip.  oc/ok: what the earlier pass left there (only a redo compares with it).
+  const bool compare = resume && reach_before != nullptr;
+  uint32_t Mq[3] = { 0, 0, 0 }, Dq[3] = { 0, 0, 0 }, ocq[4] = { 0, 0, 0, 0 }, okq[4] = { 0, 0, 0, 0 };
+#pragma unroll
+  for (int k = 0; k < 3; k++)
+    if ((int32_t)top_group - 1 - k >= 0)
+    {
+      const uint32_t i = (top_group - 1 - k) * 32 + lane;
+      Mq[k] = mlen[b + i]; Dq[k] = mdist[b + i];
+    }
+  if (compare)
+  {
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+      if ((int32_t)top_group - k >= 0)
+      {
+        const uint32_t i = (top_group - k) * 32 + lane;
+        if (i < hi) { ocq[k] = __ldcg(s.cost + b + i); okq[k] = mfin[b + i]; }
+      }
+  }
 
   for (int32_t grp = (int32_t)top_group; grp >= (int32_t)(lo / 32); grp--)
   {
@@ -283,7 +304,14 @@ __device__ __forceinline__ void dp_segment(const uint32_t* mlen, const uint16_t*
     uint32_t M = priced ? Mn : 0;
     if (M != 0 && i + M > cap_end) { M = cap_end > i ? cap_end - i : 0; if (M < kMinMatch) M = 0; }
     const uint32_t D = Dn;
-    if (grp > 0) { Mn = mlen[b + i - 32]; Dn = mdist[b + i - 32]; }   // i - 32 < start always
+    Mn = Mq[0]; Dn = Dq[0]; Mq[0] = Mq[1]; Dq[0] = Dq[1]; Mq[1] = Mq[2]; Dq[1] = Dq[2];
+    if (grp >= 4) { Mq[2] = mlen[b + i - 128]; Dq[2] = mdist[b + i - 128]; }   // below start always
+    const uint32_t old_cost = ocq[0], old_keep = okq[0];
+    if (compare)
+    {
+      ocq[0] = ocq[1]; okq[0] = okq[1]; ocq[1] = ocq[2]; okq[1] = okq[2]; ocq[2] = ocq[3]; okq[2] = okq[3];
+      if (grp >= 4) { ocq[3] = __ldcg(s.cost + b + i - 128); okq[3] = mfin[b + i - 128]; }
+    }
     v.ring_hi = min(i0 + 32 + (uint32_t)kDpRing, resume ? 0xffffffffu : start);
 
     uint32_t cur, keep;
@@ -447,9 +475,9 @@ __device__ __forceinline__ void dp_segment(const uint32_t* mlen, const uint16_t*
       // A redo may stop once it provably reproduces the earlier (speculative) pass: over a span longer than
       // anything further left can look at, the costs differ from the earlier ones by one constant, the chosen
       // lengths are identical, and a match was chosen in the span (which also pins the literal counter).
-      const uint32_t diff = cur - __ldcg(s.cost + b + i);
+      const uint32_t diff = cur - old_cost;
       const uint32_t d0 = __shfl_sync(0xffffffffu, diff, 0);
-      const bool same = __all_sync(0xffffffffu, diff == d0 && keep == mfin[b + i]);
+      const bool same = __all_sync(0xffffffffu, diff == d0 && keep == old_keep);
       if (same && (settled == 0 || d0 == settled_diff))
       {
         settled += 32; settled_diff = d0;
