@@ -477,13 +477,21 @@ __device__ __forceinline__ void dp_segment(const uint32_t* mlen, const uint16_t*
       // lengths are identical, and a match was chosen in the span (which also pins the literal counter).
       const uint32_t diff = cur - old_cost;
       const uint32_t d0 = __shfl_sync(0xffffffffu, diff, 0);
-      const bool same = __all_sync(0xffffffffu, diff == d0 && keep == old_keep);
-      if (same && (settled == 0 || d0 == settled_diff))
+      // lanes (from the lowest position up) that reproduce the earlier pass with the offset of lane 0
+      const uint32_t ok_lanes = __ballot_sync(0xffffffffu, diff == d0 && keep == old_keep);
+      const uint32_t low = ok_lanes == 0xffffffffu ? 32u : (uint32_t)__ffs((int)~ok_lanes) - 1;
+      const uint32_t low_mask = low == 32 ? 0xffffffffu : ((1u << low) - 1);
+      const bool match_here = (__ballot_sync(0xffffffffu, keep != 1) & low_mask) != 0;
+      if (low == 32 && settled != 0 && d0 == settled_diff)
       {
-        settled += 32; settled_diff = d0;
-        settled_match = settled_match || __any_sync(0xffffffffu, keep != 1);
+        settled += 32;
+        settled_match = settled_match || match_here;
       }
-      else { settled = 0; settled_match = false; }
+      else
+      {
+        // a new span starts in this group: its top is the first lane that does not fit
+        settled = low; settled_diff = d0; settled_match = match_here;
+      }
       // the span must cover everything positions further left can look at (reach_before = largest position + length left of this group)
       if (settled_match && settled >= 256 && __ldcg(reach_before + i0 / 32) <= i0 + settled && i0 >= lo + kDpRing + 256)
       {
