@@ -63,7 +63,8 @@ enum : uint32_t
   kDpSlack = SZ4_DP_SLACK,   // a boundary is only placed where no match from the left reaches further than this
   kDpOvl   = kDpWarm + 64,   // entries of a segment's warm-up overlay
   kDpURing = 512,
-  kDpSmem  = 4 * kDpRing * 4 + 5 * 48 * 4 + kDpURing * 16 + 32 * 8
+  kDpChunk = 8,              // groups of 32 positions fetched ahead together
+  kDpSmem  = 4 * kDpRing * 4 + 5 * 48 * 4 + kDpURing * 16 + 32 * 8 + 4 * kDpChunk * 32 * 4
 };
 
 // One segment of a block: own range [lo, hi) (block relative, multiples of 32; hi == block length for the
@@ -270,30 +271,42 @@ __device__ __forceinline__ void dp_segment(const uint32_t* mlen, const uint16_t*
     __syncwarp();
   }
 
-  // matches of the first group; later groups are prefetched one group ahead
-  uint32_t Mn = 0, Dn = 0;
-  { const uint32_t i = top_group * 32 + lane; if (i < start) { Mn = mlen[b + i]; Dn = mdist[b + i]; } }
-  // ... and three more groups are kept in flight behind it: a cheap group (all literals, all long runs) takes
-  // less time than a DRAM round trip.  oc/ok: what the earlier pass left there (only a redo compares with it).
+  // Matches (and, for a redo, what the earlier pass left behind) are fetched a chunk of kDpChunk groups at a
+  // time: while the warp works on one chunk out of shared memory, the loads of the chunk below it are in
+  // flight into registers.  A cheap group (all literals, all long runs) takes far less time than a DRAM
+  // round trip, so anything closer than that would make the memory latency the time per group.
   const bool compare = resume && reach_before != nullptr;
-  uint32_t Mq[3] = { 0, 0, 0 }, Dq[3] = { 0, 0, 0 }, ocq[4] = { 0, 0, 0, 0 }, okq[4] = { 0, 0, 0, 0 };
-#pragma unroll
-  for (int k = 0; k < 3; k++)
-    if ((int32_t)top_group - 1 - k >= 0)
-    {
-      const uint32_t i = (top_group - 1 - k) * 32 + lane;
-      Mq[k] = mlen[b + i]; Dq[k] = mdist[b + i];
-    }
-  if (compare)
+  uint32_t* q_m = (uint32_t*)(s_out + 32);                       // [kDpChunk][32] each, lane-private columns
+  uint32_t* q_d = q_m + kDpChunk * 32;
+  uint32_t* q_oc = q_d + kDpChunk * 32;
+  uint32_t* q_ok = q_oc + kDpChunk * 32;
+  uint32_t nM[kDpChunk], nD[kDpChunk], nOC[kDpChunk], nOK[kDpChunk];
+  auto fetch_chunk = [&](int32_t c)
   {
 #pragma unroll
-    for (int k = 0; k < 4; k++)
-      if ((int32_t)top_group - k >= 0)
+    for (uint32_t k = 0; k < kDpChunk; k++)
+    {
+      nM[k] = 0; nD[k] = 0; nOC[k] = 0; nOK[k] = 0;
+      const uint32_t i = ((uint32_t)c * kDpChunk + k) * 32 + lane;
+      if (c >= 0 && i < start)
       {
-        const uint32_t i = (top_group - k) * 32 + lane;
-        if (i < hi) { ocq[k] = __ldcg(s.cost + b + i); okq[k] = mfin[b + i]; }
+        nM[k] = mlen[b + i]; nD[k] = mdist[b + i];
+        if (compare) { nOC[k] = __ldcg(s.cost + b + i); nOK[k] = mfin[b + i]; }
       }
-  }
+    }
+  };
+  auto commit_chunk = [&]()
+  {
+#pragma unroll
+    for (uint32_t k = 0; k < kDpChunk; k++)
+    {
+      q_m[k * 32 + lane] = nM[k]; q_d[k * 32 + lane] = nD[k];
+      if (compare) { q_oc[k * 32 + lane] = nOC[k]; q_ok[k * 32 + lane] = nOK[k]; }
+    }
+  };
+  fetch_chunk((int32_t)(top_group / kDpChunk));
+  commit_chunk();
+  fetch_chunk((int32_t)(top_group / kDpChunk) - 1);
 
   for (int32_t grp = (int32_t)top_group; grp >= (int32_t)(lo / 32); grp--)
   {
@@ -301,17 +314,17 @@ __device__ __forceinline__ void dp_segment(const uint32_t* mlen, const uint16_t*
     const uint32_t i = i0 + lane;                                // this lane's position (block relative)
     const bool exists = i < start;
     const bool priced = exists && i <= last_priced;
-    uint32_t M = priced ? Mn : 0;
-    if (M != 0 && i + M > cap_end) { M = cap_end > i ? cap_end - i : 0; if (M < kMinMatch) M = 0; }
-    const uint32_t D = Dn;
-    Mn = Mq[0]; Dn = Dq[0]; Mq[0] = Mq[1]; Dq[0] = Dq[1]; Mq[1] = Mq[2]; Dq[1] = Dq[2];
-    if (grp >= 4) { Mq[2] = mlen[b + i - 128]; Dq[2] = mdist[b + i - 128]; }   // below start always
-    const uint32_t old_cost = ocq[0], old_keep = okq[0];
-    if (compare)
+    if (((uint32_t)grp & (kDpChunk - 1)) == kDpChunk - 1 && (uint32_t)grp != top_group)
     {
-      ocq[0] = ocq[1]; okq[0] = okq[1]; ocq[1] = ocq[2]; okq[1] = okq[2]; ocq[2] = ocq[3]; okq[2] = okq[3];
-      if (grp >= 4) { ocq[3] = __ldcg(s.cost + b + i - 128); okq[3] = mfin[b + i - 128]; }
+      commit_chunk();                                            // the chunk that starts here was fetched a chunk ago
+      fetch_chunk(grp / (int32_t)kDpChunk - 1);
     }
+    const uint32_t qi = ((uint32_t)grp & (kDpChunk - 1)) * 32 + lane;
+    uint32_t M = priced ? q_m[qi] : 0;
+    if (M != 0 && i + M > cap_end) { M = cap_end > i ? cap_end - i : 0; if (M < kMinMatch) M = 0; }
+    const uint32_t D = q_d[qi];
+    uint32_t old_cost = 0, old_keep = 0;
+    if (compare) { old_cost = q_oc[qi]; old_keep = q_ok[qi]; }
     v.ring_hi = min(i0 + 32 + (uint32_t)kDpRing, resume ? 0xffffffffu : start);
 
     uint32_t cur, keep;

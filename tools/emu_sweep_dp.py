@@ -1,0 +1,26 @@
+import time
+import numpy as np
+from emu_lib import emu_compressor
+from oracle_lib import oracle_compress
+from smallz4_b200 import corpus
+BS=131072
+c = emu_compressor(block_size=BS, batch_blocks=2)
+bad=0
+def chk(tag,data,lvl):
+    global bad
+    out = c.compress(data, level=lvl)
+    ref,st = oracle_compress(data, lvl, block_size=BS)
+    ok = out==ref; bad += (not ok)
+    print(tag,lvl,len(data),len(out),len(ref),'OK' if ok else 'MISMATCH',f'redos={c.last_dp_redos()},{c.last_path_redos()}',flush=True)
+rnd=lambda n,s: corpus.make('random',n,s).tobytes()
+txt=lambda n,s: corpus.make('text',n,s).tobytes()
+binr=lambda n,s: corpus.make('binary',n,s).tobytes()
+for lvl in [9,5]:
+    chk('zeros+random', bytes(50000)+rnd(30000,1)+bytes(40000)+rnd(9000,2)+txt(30000,3), lvl)
+    chk('text+random', txt(40000,1)+rnd(20000,1)+txt(40000,2)+rnd(20000,3)+txt(30000,4), lvl)
+    chk('binary+random', binr(40000,1)+rnd(20000,1)+binr(40000,2)+rnd(5000,3)+binr(30000,4), lvl)
+    chk('runs+random', corpus.make('runs',60000,3).tobytes()+rnd(20000,1)+corpus.make('runs',60000,4).tobytes()+rnd(7000,5)+b'\x09'*70000+rnd(6000,6)+txt(8000,1), lvl)
+    for seed in [1,2,3,4]:
+        chk('mixed',corpus.make('mixed',400000,seed).tobytes(),lvl)
+chk('random',rnd(200000,9),9)
+print('BAD',bad)
