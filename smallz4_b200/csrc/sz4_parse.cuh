@@ -64,12 +64,16 @@ enum : uint32_t
   kDpOvl   = kDpWarm + 64,   // entries of a segment's warm-up overlay
   kDpURing = 512,
   kDpChunk = 8,              // groups of 32 positions fetched ahead together
-  kDpSmem  = 4 * kDpRing * 4 + 5 * 48 * 4 + kDpURing * 16 + 32 * 8 + 4 * kDpChunk * 32 * 4
+  kDpSmem  = 4 * kDpRing * 4 + 5 * 48 * 4 + kDpURing * 16 + 32 * 8 + 4 * kDpChunk * 32 * 4,
+  kDpSmemSpec = kDpSmem - 2 * kDpChunk * 32 * 4   // a first pass has nothing to compare with: no queue for the earlier results
 };
 
 // One segment of a block: own range [lo, hi) (block relative, multiples of 32; hi == block length for the
 // top segment).  reach = largest i + len[i] over i < hi: positions left of hi never look beyond it.
-struct DpTask { uint32_t lo, hi, reach, pad_; };
+// run_end != 0: hi lies inside a long run whose positions all take their match unpriced (smallz4.h:410-416) and all
+// end at run_end; such matches are left out of reach (their cost is cost[run_end] plus a function of the length,
+// so the segment prices itself relative to cost[run_end] := 0, see dp_segment).
+struct DpTask { uint32_t lo, hi, reach, run_end; };
 // until_bump after the positions >= hi / >= lo were done; cum = offset of this segment's costs to the true ones
 struct DpState { uint32_t ub_hi, ub_lo, redone, cum; };
 struct DpOverlay { uint32_t* cost; uint32_t* st5; uint32_t* st6; uint32_t* st7; };   // warm-up results, kDpOvl each
@@ -207,15 +211,19 @@ __device__ __forceinline__ void dp_steps(uint32_t lane, uint32_t i0, uint32_t la
 __device__ __forceinline__ void dp_segment(const uint32_t* mlen, const uint16_t* mdist, uint32_t* mfin, DpScratch s, DpOverlay ovl,
                                            uint32_t b, uint32_t n, uint32_t lo, uint32_t hi, bool resume, uint32_t ub_resume,
                                            unsigned char* smem, uint32_t& ub_hi, uint32_t& ub_lo, const uint32_t* reach_before = nullptr,
-                                           bool* stopped = nullptr)
+                                           bool* stopped = nullptr, uint32_t run_end = 0)
 {
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t start = resume ? hi : min(hi + (uint32_t)kDpWarm, n);
   const bool true_end = (start == n) && !resume;
   // a cold start prices the positions as if the block ended at `start` (smallz4.h:389: the last five are free,
   // matches end five bytes before the end); at the real end this is the reference's own rule
-  const uint32_t last_priced = resume ? 0xffffffffu : start - (1 + kEndLiterals);
+  // (a cold start inside a long run, run_end != 0, is exact instead: every position of the warm-up zone takes
+  // its match to run_end unpriced, so its cost is a function of the distance to run_end alone)
+  const uint32_t run_e = resume ? 0 : run_end;
+  const uint32_t last_priced = (resume || run_e != 0) ? 0xffffffffu : start - (1 + kEndLiterals);
   const uint32_t cap_end = (resume || true_end) ? 0xffffffffu : start - kEndLiterals;
+  bool bad = false;                                              // the run did not look as the plan assumed
   const uint32_t top_group = (start - 1) / 32;
 
   uint32_t* r_cost = (uint32_t*)smem;
@@ -238,7 +246,7 @@ __device__ __forceinline__ void dp_segment(const uint32_t* mlen, const uint16_t*
   uint32_t prv = 0;                                              // cost of (group+1)*32 + lane
   uint32_t p5 = 0xffffffffu, p6a = 0xffffffffu, p6b = 0xffffffffu;   // st5 of group+1, st6 of group+1 / group+2
   bool have_prev = false;                                        // a group above this one exists
-  uint32_t far_end = 0xffffffffu, far_cost = 0;                  // last end position of an unpriced long run and its cost
+  uint32_t far_end = run_e != 0 ? run_e : 0xffffffffu, far_cost = 0;   // last end position of an unpriced long run and its cost
   uint32_t settled = 0;                                          // resume: positions in a row that reproduce the earlier result
   bool settled_match = false, early_stop = false;
   uint32_t settled_diff = 0;
@@ -321,8 +329,15 @@ __device__ __forceinline__ void dp_segment(const uint32_t* mlen, const uint16_t*
     }
     const uint32_t qi = ((uint32_t)grp & (kDpChunk - 1)) * 32 + lane;
     uint32_t M = priced ? q_m[qi] : 0;
-    if (M != 0 && i + M > cap_end) { M = cap_end > i ? cap_end - i : 0; if (M < kMinMatch) M = 0; }
     const uint32_t D = q_d[qi];
+    const bool to_run_end = run_e != 0 && M >= kSameLetter && D == 1 && i + M == run_e;
+    if (M != 0 && i + M > cap_end && !to_run_end)
+    {
+      if (run_e != 0 && M >= kSameLetter && D == 1) bad = true;  // an unpriced match to somewhere else: not covered by `reach`
+      M = cap_end > i ? cap_end - i : 0;
+      if (M < kMinMatch) M = 0;
+    }
+    if (run_e != 0 && i0 >= hi && !__all_sync(0xffffffffu, to_run_end)) bad = true;
     uint32_t old_cost = 0, old_keep = 0;
     if (compare) { old_cost = q_oc[qi]; old_keep = q_ok[qi]; }
     v.ring_hi = min(i0 + 32 + (uint32_t)kDpRing, resume ? 0xffffffffu : start);
@@ -349,7 +364,7 @@ __device__ __forceinline__ void dp_segment(const uint32_t* mlen, const uint16_t*
         forced = true;                                             // smallz4.h:410-416
         // inside one long run every position's match ends at the same place: remember that cost
         const uint32_t end = i + M;
-        if (end != far_end) { far_end = end; far_cost = v.cost(end); }
+        if (end != far_end) { far_end = end; far_cost = to_run_end ? 0u : v.cost(end); }
         bc = far_cost + 1 + 2 + 1 + (M - 19) / 255;
         bl = M;
       }
@@ -537,6 +552,7 @@ __device__ __forceinline__ void dp_segment(const uint32_t* mlen, const uint16_t*
   }
   if (stopped) *stopped = early_stop;
   if (!early_stop) ub_lo = until_bump;
+  if (__any_sync(0xffffffffu, bad)) ub_hi = 0xfffffffeu;          // never equals a literal counter: the segment is redone
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -550,28 +566,41 @@ __device__ __forceinline__ void dp_segment(const uint32_t* mlen, const uint16_t*
 // recurrence only uses differences); otherwise that segment is priced again from the true state.
 // Exactness never depends on the guess -- only the speed does.
 // ---------------------------------------------------------------------------------------------
-// reach of every group of 32 positions: max over its positions of (position + found match length), 0 if none.
-// One warp per 1024 positions; lane g ends up with the value of group g and the 32 values are stored coalesced.
+// Per group of 32 positions: reach = max over its positions of (position + found match length), 0 if none;
+// reach_nf = the same without the unpriced long-run matches (length >= 65299 at distance 1, smallz4.h:410);
+// run_end = where those matches end if all 32 positions have one and they all end at the same place, else 0.
+// One warp per 1024 positions; lane g ends up with the values of group g and they are stored coalesced.
 __global__ void __launch_bounds__(256)
-k_dp_group_reach(const uint32_t* mlen, uint32_t* group_reach, uint32_t groups_per_block, Geom g)
+k_dp_group_reach(const uint32_t* mlen, const uint16_t* mdist, uint32_t* group_reach, uint32_t* group_reach_nf, uint32_t* group_run_end,
+                 uint32_t groups_per_block, Geom g)
 {
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const uint32_t chunks_per_block = (groups_per_block + 31) / 32;
   const uint32_t j = warp / chunks_per_block, c = warp % chunks_per_block;
   if (j >= g.n_blocks) return;
   const uint32_t b = block_begin(g, j), n = block_len(g, j);
-  uint32_t mine = 0;
+  uint32_t mine = 0, mine_nf = 0, mine_run = 0;
 #pragma unroll 4
   for (uint32_t k = 0; k < 32; k++)
   {
     const uint32_t i = (c * 32 + k) * 32 + lane;
-    uint32_t r = 0;
-    if (i < n) { const uint32_t M = mlen[b + i]; if (M > 1) r = i + M; }
+    uint32_t r = 0, rn = 0, e = 0;
+    if (i < n)
+    {
+      const uint32_t M = mlen[b + i];
+      if (M > 1) { r = i + M; if (M >= kSameLetter && mdist[b + i] == 1) e = r; else rn = r; }
+    }
     r = __reduce_max_sync(0xffffffffu, r);
-    if (lane == k) mine = r;
+    rn = __reduce_max_sync(0xffffffffu, rn);
+    const uint32_t e_hi = __reduce_max_sync(0xffffffffu, e), e_lo = __reduce_min_sync(0xffffffffu, e);
+    if (lane == k) { mine = r; mine_nf = rn; mine_run = e_hi == e_lo ? e_hi : 0; }
   }
   const uint32_t grp = c * 32 + lane;
-  if (grp < groups_per_block) group_reach[(size_t)j * groups_per_block + grp] = mine;
+  if (grp < groups_per_block)
+  {
+    const size_t at = (size_t)j * groups_per_block + grp;
+    group_reach[at] = mine; group_reach_nf[at] = mine_nf; group_run_end[at] = mine_run;
+  }
 }
 
 // One warp per block: exclusive prefix maximum of the group reaches, 32 groups per step, and a boundary
@@ -579,7 +608,8 @@ k_dp_group_reach(const uint32_t* mlen, uint32_t* group_reach, uint32_t groups_pe
 // (kernels that give one warp a sequential job pack four such warps into a CTA: a warp's scheduler is
 // its index in the CTA modulo 4, so single-warp CTAs would all queue on the first of the SM's four schedulers)
 __global__ void __launch_bounds__(128)
-k_dp_plan(uint32_t* group_reach, uint32_t groups_per_block, DpTask* tasks, uint32_t* task_count, uint32_t max_seg, Geom g)
+k_dp_plan(uint32_t* group_reach, const uint32_t* group_reach_nf, const uint32_t* group_run_end, uint32_t groups_per_block,
+          DpTask* tasks, uint32_t* task_count, uint32_t max_seg, Geom g)
 {
   const uint32_t j = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (j >= g.n_blocks) return;
@@ -588,28 +618,40 @@ k_dp_plan(uint32_t* group_reach, uint32_t groups_per_block, DpTask* tasks, uint3
   DpTask* out = tasks + (size_t)j * max_seg;
   if (n <= kEndNoMatch) { if (lane == 0) task_count[j] = 0; return; }     // smallz4.h:755
   uint32_t* gr = group_reach + (size_t)j * groups_per_block;   // in: reach of each group; out: reach of everything left of it
+  const uint32_t* gn = group_reach_nf + (size_t)j * groups_per_block;
+  const uint32_t* ge = group_run_end + (size_t)j * groups_per_block;
   const uint32_t groups = (n + 31) / 32;
-  uint32_t count = 0, last = 0, carry = 0;
-  uint32_t nxt = lane < groups ? gr[lane] : 0;
+  uint32_t count = 0, last = 0, carry = 0, carry_nf = 0;
+  uint32_t nxt = lane < groups ? gr[lane] : 0, nxt_nf = lane < groups ? gn[lane] : 0;
   for (uint32_t g0 = 0; g0 < groups; g0 += 32)
   {
-    const uint32_t mine = nxt;
-    if (g0 + 32 + lane < groups) nxt = gr[g0 + 32 + lane]; else nxt = 0;
+    const uint32_t mine = nxt, mine_nf = nxt_nf;
+    if (g0 + 32 + lane < groups) { nxt = gr[g0 + 32 + lane]; nxt_nf = gn[g0 + 32 + lane]; } else { nxt = 0; nxt_nf = 0; }
     // inclusive prefix max over the 32 groups, then shift by one lane: reach of everything left of group g0+lane
-    uint32_t incl = mine;
+    uint32_t incl = mine, incl_nf = mine_nf;
 #pragma unroll
     for (uint32_t d = 1; d < 32; d <<= 1)
     {
-      uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-      if (lane >= d) incl = max(incl, t);
+      uint32_t t = __shfl_up_sync(0xffffffffu, incl, d), tn = __shfl_up_sync(0xffffffffu, incl_nf, d);
+      if (lane >= d) { incl = max(incl, t); incl_nf = max(incl_nf, tn); }
     }
-    uint32_t before = __shfl_up_sync(0xffffffffu, incl, 1);
+    uint32_t before = __shfl_up_sync(0xffffffffu, incl, 1), before_nf = __shfl_up_sync(0xffffffffu, incl_nf, 1);
     before = lane == 0 ? carry : max(before, carry);
+    before_nf = lane == 0 ? carry_nf : max(before_nf, carry_nf);
     if (g0 + lane < groups) gr[g0 + lane] = before;
     const uint32_t x0 = (g0 + lane) * 32;
-    const bool fits = g0 + lane < groups && x0 > 0 && x0 + 64 <= n && before <= x0 + kDpSlack;
+    const bool inside = g0 + lane < groups && x0 > 0 && x0 + 64 <= n;
+    const bool fits = inside && before <= x0 + kDpSlack;
+    // ... or the boundary lies inside a long run of unpriced matches that all end at the same place, its whole
+    // warm-up zone does too, and nothing else reaches across
+    uint32_t run_end = 0;
+    if (inside && !fits && before_nf <= x0 + kDpSlack && g0 + lane + kDpWarm / 32 + 1 < groups)
+    {
+      const uint32_t e = ge[g0 + lane];
+      if (e != 0 && ge[g0 + lane + kDpWarm / 32 + 1] == e) run_end = e;
+    }
     // at most a few boundaries per 1024 positions: take them in order
-    uint32_t cand = __ballot_sync(0xffffffffu, fits);
+    uint32_t cand = __ballot_sync(0xffffffffu, fits || run_end != 0);
     while (cand)
     {
       const int l = __ffs((int)cand) - 1;
@@ -617,15 +659,17 @@ k_dp_plan(uint32_t* group_reach, uint32_t groups_per_block, DpTask* tasks, uint3
       cand &= cand - 1;
       if (xb - last >= kDpSeg && count + 2 < max_seg)
       {
-        const uint32_t reach = __shfl_sync(0xffffffffu, before, l);
-        if (lane == 0) { DpTask t; t.lo = last; t.hi = xb; t.reach = reach; t.pad_ = 0; out[count] = t; }
+        const uint32_t e = __shfl_sync(0xffffffffu, run_end, l);
+        const uint32_t reach = __shfl_sync(0xffffffffu, e != 0 ? before_nf : before, l);
+        if (lane == 0) { DpTask t; t.lo = last; t.hi = xb; t.reach = reach; t.run_end = e; out[count] = t; }
         count++;
         last = xb;
       }
     }
     carry = max(carry, __shfl_sync(0xffffffffu, incl, 31));
+    carry_nf = max(carry_nf, __shfl_sync(0xffffffffu, incl_nf, 31));
   }
-  if (lane == 0) { DpTask t; t.lo = last; t.hi = n; t.reach = n; t.pad_ = 0; out[count] = t; task_count[j] = count + 1; }
+  if (lane == 0) { DpTask t; t.lo = last; t.hi = n; t.reach = n; t.run_end = 0; out[count] = t; task_count[j] = count + 1; }
 }
 
 __device__ __forceinline__ DpOverlay overlay_of(uint32_t* base, uint32_t task_index)
@@ -651,7 +695,7 @@ k_dp_spec(const uint32_t* mlen, const uint16_t* mdist, uint32_t* mfin, DpScratch
   const long long t0 = clock64();
 #endif
   dp_segment(mlen, mdist, mfin, s, overlay_of(overlays, ti), block_begin(g, j), block_len(g, j), t.lo, t.hi,
-             false, 0, smem + warp * kDpSmem, ub_hi, ub_lo);
+             false, 0, smem + warp * kDpSmem, ub_hi, ub_lo, nullptr, nullptr, t.run_end);
   if ((threadIdx.x & 31) == 0)
   {
     DpState st; st.ub_hi = ub_hi; st.ub_lo = ub_lo; st.redone = 0; st.cum = 0; states[ti] = st;

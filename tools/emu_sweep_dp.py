@@ -1,3 +1,6 @@
+import sys, os
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'tests'))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..'))
 import time
 import numpy as np
 from emu_lib import emu_compressor
@@ -23,4 +26,8 @@ for lvl in [9,5]:
     for seed in [1,2,3,4]:
         chk('mixed',corpus.make('mixed',400000,seed).tobytes(),lvl)
 chk('random',rnd(200000,9),9)
+for lvl in [9]:   # long runs are slow in the emulator (minutes each)
+    chk('zeros+text', bytes(120000)+txt(30000,5)+b'\x07'*100000+txt(12144,6), lvl)
+    chk('zeros-rand-zeros', bytes(90000)+rnd(100,3)+bytes(90000)+rnd(50,4)+bytes(81994), lvl)
+
 print('BAD',bad)
