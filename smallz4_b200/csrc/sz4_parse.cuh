@@ -73,7 +73,20 @@ enum : uint32_t
 // run_end != 0: hi lies inside a long run whose positions all take their match unpriced (smallz4.h:410-416) and all
 // end at run_end; such matches are left out of reach (their cost is cost[run_end] plus a function of the length,
 // so the segment prices itself relative to cost[run_end] := 0, see dp_segment).
-struct DpTask { uint32_t lo, hi, reach, run_end; };
+// ub_start != 0: the warm-up starts in a stretch without any match candidate; ub_start is the literal counter
+// (until_bump) there if the stretch runs to the end of the block (exact) or if the first candidate behind it
+// is taken (a guess, checked like everything else by k_dp_verify).
+struct DpTask
+{
+  uint32_t lo, hi, reach, aux;                                   // aux = run_end | ub_start << 24
+  __device__ __forceinline__ uint32_t run_end() const { return aux & 0xffffffu; }
+  __device__ __forceinline__ uint32_t ub_start() const { return aux >> 24; }
+};
+// literal counter after k literal decisions that follow a state with `first` decisions left until the next length byte
+__device__ __forceinline__ uint32_t until_bump_after(uint32_t first, uint32_t k)
+{
+  return k < first ? first - k : 255u - ((k - first) % 255u);
+}
 // until_bump after the positions >= hi / >= lo were done; cum = offset of this segment's costs to the true ones
 struct DpState { uint32_t ub_hi, ub_lo, redone, cum; };
 struct DpOverlay { uint32_t* cost; uint32_t* st5; uint32_t* st6; uint32_t* st7; };   // warm-up results, kDpOvl each
@@ -211,7 +224,7 @@ __device__ __forceinline__ void dp_steps(uint32_t lane, uint32_t i0, uint32_t la
 __device__ __forceinline__ void dp_segment(const uint32_t* mlen, const uint16_t* mdist, uint32_t* mfin, DpScratch s, DpOverlay ovl,
                                            uint32_t b, uint32_t n, uint32_t lo, uint32_t hi, bool resume, uint32_t ub_resume,
                                            unsigned char* smem, uint32_t& ub_hi, uint32_t& ub_lo, const uint32_t* reach_before = nullptr,
-                                           bool* stopped = nullptr, uint32_t run_end = 0)
+                                           bool* stopped = nullptr, uint32_t run_end = 0, uint32_t ub_start = 0)
 {
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t start = resume ? hi : min(hi + (uint32_t)kDpWarm, n);
@@ -220,8 +233,10 @@ __device__ __forceinline__ void dp_segment(const uint32_t* mlen, const uint16_t*
   // matches end five bytes before the end); at the real end this is the reference's own rule
   // (a cold start inside a long run, run_end != 0, is exact instead: every position of the warm-up zone takes
   // its match to run_end unpriced, so its cost is a function of the distance to run_end alone)
+  // (a cold start in a stretch without match candidates, ub_start != 0, takes over the literal counter the plan worked out)
   const uint32_t run_e = resume ? 0 : run_end;
-  const uint32_t last_priced = (resume || run_e != 0) ? 0xffffffffu : start - (1 + kEndLiterals);
+  const uint32_t ub_cold = (resume || true_end || run_e != 0) ? 0 : ub_start;
+  const uint32_t last_priced = (resume || run_e != 0 || ub_cold != 0) ? 0xffffffffu : start - (1 + kEndLiterals);
   const uint32_t cap_end = (resume || true_end) ? 0xffffffffu : start - kEndLiterals;
   bool bad = false;                                              // the run did not look as the plan assumed
   const uint32_t top_group = (start - 1) / 32;
@@ -241,7 +256,7 @@ __device__ __forceinline__ void dp_segment(const uint32_t* mlen, const uint16_t*
   for (uint32_t k = lane; k < 5 * 48; k += 32) lvl[k] = 0xffffffffu;
   __syncwarp();
 
-  uint32_t until_bump = 15 - kEndLiterals;                       // numLiterals starts at 5 (smallz4.h:387)
+  uint32_t until_bump = ub_cold != 0 ? ub_cold : 15 - kEndLiterals;   // numLiterals starts at 5 (smallz4.h:387)
   uint32_t next_cost = 0;                                        // cost[i+1], uniform
   uint32_t prv = 0;                                              // cost of (group+1)*32 + lane
   uint32_t p5 = 0xffffffffu, p6a = 0xffffffffu, p6b = 0xffffffffu;   // st5 of group+1, st6 of group+1 / group+2
@@ -572,34 +587,36 @@ __device__ __forceinline__ void dp_segment(const uint32_t* mlen, const uint16_t*
 // One warp per 1024 positions; lane g ends up with the values of group g and they are stored coalesced.
 __global__ void __launch_bounds__(256)
 k_dp_group_reach(const uint32_t* mlen, const uint16_t* mdist, uint32_t* group_reach, uint32_t* group_reach_nf, uint32_t* group_run_end,
-                 uint32_t groups_per_block, Geom g)
+                 uint32_t* group_first, uint32_t groups_per_block, Geom g)
 {
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const uint32_t chunks_per_block = (groups_per_block + 31) / 32;
   const uint32_t j = warp / chunks_per_block, c = warp % chunks_per_block;
   if (j >= g.n_blocks) return;
   const uint32_t b = block_begin(g, j), n = block_len(g, j);
-  uint32_t mine = 0, mine_nf = 0, mine_run = 0;
+  uint32_t mine = 0, mine_nf = 0, mine_run = 0, mine_first = 0xffffffffu;   // first = first position with a match candidate
 #pragma unroll 4
   for (uint32_t k = 0; k < 32; k++)
   {
     const uint32_t i = (c * 32 + k) * 32 + lane;
-    uint32_t r = 0, rn = 0, e = 0;
+    uint32_t r = 0, rn = 0, e = 0, f = 0xffffffffu;
     if (i < n)
     {
       const uint32_t M = mlen[b + i];
       if (M > 1) { r = i + M; if (M >= kSameLetter && mdist[b + i] == 1) e = r; else rn = r; }
+      if (M >= kMinMatch) f = i;
     }
+    f = __reduce_min_sync(0xffffffffu, f);
     r = __reduce_max_sync(0xffffffffu, r);
     rn = __reduce_max_sync(0xffffffffu, rn);
     const uint32_t e_hi = __reduce_max_sync(0xffffffffu, e), e_lo = __reduce_min_sync(0xffffffffu, e);
-    if (lane == k) { mine = r; mine_nf = rn; mine_run = e_hi == e_lo ? e_hi : 0; }
+    if (lane == k) { mine = r; mine_nf = rn; mine_run = e_hi == e_lo ? e_hi : 0; mine_first = f; }
   }
   const uint32_t grp = c * 32 + lane;
   if (grp < groups_per_block)
   {
     const size_t at = (size_t)j * groups_per_block + grp;
-    group_reach[at] = mine; group_reach_nf[at] = mine_nf; group_run_end[at] = mine_run;
+    group_reach[at] = mine; group_reach_nf[at] = mine_nf; group_run_end[at] = mine_run; group_first[at] = mine_first;
   }
 }
 
@@ -608,8 +625,8 @@ k_dp_group_reach(const uint32_t* mlen, const uint16_t* mdist, uint32_t* group_re
 // (kernels that give one warp a sequential job pack four such warps into a CTA: a warp's scheduler is
 // its index in the CTA modulo 4, so single-warp CTAs would all queue on the first of the SM's four schedulers)
 __global__ void __launch_bounds__(128)
-k_dp_plan(uint32_t* group_reach, const uint32_t* group_reach_nf, const uint32_t* group_run_end, uint32_t groups_per_block,
-          DpTask* tasks, uint32_t* task_count, uint32_t max_seg, Geom g)
+k_dp_plan(uint32_t* group_reach, const uint32_t* group_reach_nf, const uint32_t* group_run_end, uint32_t* group_first,
+          uint32_t groups_per_block, DpTask* tasks, uint32_t* task_count, uint32_t max_seg, Geom g)
 {
   const uint32_t j = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (j >= g.n_blocks) return;
@@ -620,7 +637,25 @@ k_dp_plan(uint32_t* group_reach, const uint32_t* group_reach_nf, const uint32_t*
   uint32_t* gr = group_reach + (size_t)j * groups_per_block;   // in: reach of each group; out: reach of everything left of it
   const uint32_t* gn = group_reach_nf + (size_t)j * groups_per_block;
   const uint32_t* ge = group_run_end + (size_t)j * groups_per_block;
+  uint32_t* gf = group_first + (size_t)j * groups_per_block;   // in: first candidate of each group; out: first one at or behind it
   const uint32_t groups = (n + 31) / 32;
+  {
+    uint32_t behind = 0xffffffffu;
+    for (int32_t g0 = (int32_t)((groups - 1) & ~31u); g0 >= 0; g0 -= 32)
+    {
+      uint32_t f = (uint32_t)g0 + lane < groups ? gf[(uint32_t)g0 + lane] : 0xffffffffu;
+#pragma unroll
+      for (uint32_t d = 1; d < 32; d <<= 1)
+      {
+        const uint32_t t = __shfl_down_sync(0xffffffffu, f, d);
+        if (lane + d < 32) f = min(f, t);
+      }
+      f = min(f, behind);
+      if ((uint32_t)g0 + lane < groups) gf[(uint32_t)g0 + lane] = f;
+      behind = __shfl_sync(0xffffffffu, f, 0);
+    }
+    __syncwarp();
+  }
   uint32_t count = 0, last = 0, carry = 0, carry_nf = 0;
   uint32_t nxt = lane < groups ? gr[lane] : 0, nxt_nf = lane < groups ? gn[lane] : 0;
   for (uint32_t g0 = 0; g0 < groups; g0 += 32)
@@ -661,7 +696,19 @@ k_dp_plan(uint32_t* group_reach, const uint32_t* group_reach_nf, const uint32_t*
       {
         const uint32_t e = __shfl_sync(0xffffffffu, run_end, l);
         const uint32_t reach = __shfl_sync(0xffffffffu, e != 0 ? before_nf : before, l);
-        if (lane == 0) { DpTask t; t.lo = last; t.hi = xb; t.reach = reach; t.run_end = e; out[count] = t; }
+        if (lane == 0)
+        {
+          // literal counter at the top of the warm-up zone when no match candidate is near (see DpTask)
+          uint32_t ub = 0;
+          const uint32_t top = xb + kDpWarm;
+          if (e == 0 && top + 64 <= n)
+          {
+            const uint32_t c = gf[top / 32];
+            if (c == 0xffffffffu) ub = until_bump_after(15 - kEndLiterals, n - kEndLiterals - top);
+            else if (c - top >= 64) ub = until_bump_after(15, c - top);
+          }
+          DpTask t; t.lo = last; t.hi = xb; t.reach = reach; t.aux = e | (ub << 24); out[count] = t;
+        }
         count++;
         last = xb;
       }
@@ -669,7 +716,7 @@ k_dp_plan(uint32_t* group_reach, const uint32_t* group_reach_nf, const uint32_t*
     carry = max(carry, __shfl_sync(0xffffffffu, incl, 31));
     carry_nf = max(carry_nf, __shfl_sync(0xffffffffu, incl_nf, 31));
   }
-  if (lane == 0) { DpTask t; t.lo = last; t.hi = n; t.reach = n; t.run_end = 0; out[count] = t; task_count[j] = count + 1; }
+  if (lane == 0) { DpTask t; t.lo = last; t.hi = n; t.reach = n; t.aux = 0; out[count] = t; task_count[j] = count + 1; }
 }
 
 __device__ __forceinline__ DpOverlay overlay_of(uint32_t* base, uint32_t task_index)
@@ -695,7 +742,7 @@ k_dp_spec(const uint32_t* mlen, const uint16_t* mdist, uint32_t* mfin, DpScratch
   const long long t0 = clock64();
 #endif
   dp_segment(mlen, mdist, mfin, s, overlay_of(overlays, ti), block_begin(g, j), block_len(g, j), t.lo, t.hi,
-             false, 0, smem + warp * kDpSmem, ub_hi, ub_lo, nullptr, nullptr, t.run_end);
+             false, 0, smem + warp * kDpSmem, ub_hi, ub_lo, nullptr, nullptr, t.run_end(), t.ub_start());
   if ((threadIdx.x & 31) == 0)
   {
     DpState st; st.ub_hi = ub_hi; st.ub_lo = ub_lo; st.redone = 0; st.cum = 0; states[ti] = st;

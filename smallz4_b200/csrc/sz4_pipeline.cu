@@ -288,13 +288,14 @@ static int run_batch(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
     CK(cudaMemcpyAsync(mfin, mlen, (size_t)N * 4, cudaMemcpyDeviceToDevice, ctx->stream));
     const uint32_t groups_per_block = g.block_size / 32;
     const size_t n_groups = (size_t)g.n_blocks * groups_per_block;
-    RSV(dp_reach, 3 * (n_groups * 4 + 64));
+    RSV(dp_reach, 4 * (n_groups * 4 + 64));
     uint32_t* reach_all = (uint32_t*)ctx->dp_reach.p;
     uint32_t* reach_nf = reach_all + n_groups + 16;
     uint32_t* run_ends = reach_nf + n_groups + 16;
+    uint32_t* first_cand = run_ends + n_groups + 16;
     LAUNCH(ctx, k_dp_group_reach, div_up((uint64_t)g.n_blocks * div_up(groups_per_block, 32) * 32, 256), 256, 0,
-           (const uint32_t*)mlen, (const uint16_t*)mdist, reach_all, reach_nf, run_ends, groups_per_block, g);
-    LAUNCH(ctx, k_dp_plan, div_up(g.n_blocks, 4), 128, 0, reach_all, (const uint32_t*)reach_nf, (const uint32_t*)run_ends,
+           (const uint32_t*)mlen, (const uint16_t*)mdist, reach_all, reach_nf, run_ends, first_cand, groups_per_block, g);
+    LAUNCH(ctx, k_dp_plan, div_up(g.n_blocks, 4), 128, 0, reach_all, (const uint32_t*)reach_nf, (const uint32_t*)run_ends, first_cand,
            groups_per_block, (DpTask*)ctx->dp_tasks.p, (uint32_t*)ctx->dp_count.p, max_seg, g);
     LAUNCH(ctx, k_dp_spec, n_tasks, 32, kDpSmemSpec, (const uint32_t*)mlen, (const uint16_t*)mdist, mfin, dp, (const DpTask*)ctx->dp_tasks.p,
            (const uint32_t*)ctx->dp_count.p, (DpState*)ctx->dp_states.p, (uint32_t*)ctx->dp_overlays.p, max_seg, (uint32_t*)ctx->dp_redo.p, g);

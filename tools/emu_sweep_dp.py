@@ -26,7 +26,9 @@ for lvl in [9,5]:
     for seed in [1,2,3,4]:
         chk('mixed',corpus.make('mixed',400000,seed).tobytes(),lvl)
 chk('random',rnd(200000,9),9)
-for lvl in [9]:   # long runs are slow in the emulator (minutes each)
+chk('random-tail',txt(70000,9)+rnd(250000,9),9)
+chk('random-gaps',rnd(100000,1)+txt(300,2)+rnd(70000,3)+txt(3000,2)+rnd(90000,4),9)
+for lvl in ([] if 'quick' in sys.argv else [9]):   # long runs are slow in the emulator (minutes each)
     chk('zeros+text', bytes(120000)+txt(30000,5)+b'\x07'*100000+txt(12144,6), lvl)
     chk('zeros-rand-zeros', bytes(90000)+rnd(100,3)+bytes(90000)+rnd(50,4)+bytes(81994), lvl)
 
