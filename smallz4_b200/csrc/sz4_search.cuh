@@ -214,6 +214,49 @@ __device__ __forceinline__ bool walk_stretch(const SearchView& v, const uint32_t
 enum : uint32_t { kIdle = 0, kWalk = 1, kCheck = 2, kStretch = 3, kFinish = 4 };
 enum : uint32_t { kFastHops = 8, kStretchMin = 8 };
 
+// The rejecting path of the walk (smallz4.h:192-233) for up to `hops` candidates per lane; see k_search.
+// kRuns = false: no walking lane of the warp is inside a byte run, the stretch bookkeeping is left out.
+template <bool kRuns>
+__device__ __forceinline__ void fast_hops_loop(const SearchView& v, uint32_t hops, uint32_t& state, uint32_t& total, uint32_t& hop,
+                                               uint32_t& ones, uint32_t run, bool fast, uint32_t tail, smem_addr cbase, smem_addr dl)
+{
+#pragma unroll 1
+  for (uint32_t it = 0; it < hops; it++)
+  {
+    const bool walking = state == kWalk;
+    const uint32_t tot2 = total + hop;
+    const bool ends = hop == 0 || tot2 > kWindow;                  // smallz4.h:192,196
+    const bool go = walking && !ends;
+    // chain entry of the candidate q = p - tot2 (at 65535 its value ends the walk either way)
+    const uint32_t hop2 = go ? lds_u16(cbase - 2 * tot2) : 0;
+    // the candidate's bytes q+len-3 .. q+len against p's: the group the reference compares first
+    // (unaligned 32-bit read from shared memory: two aligned words and a funnel shift)
+    const smem_addr a = dl - tot2;
+    const uint32_t sh = (uint32_t)(a - v.s_data) & 3u;
+    const smem_addr w = a - sh;
+    const bool peek = go && fast;
+    const uint32_t w0 = peek ? lds_u32(w) : 0, w1 = peek ? lds_u32(w + 4) : 0;
+    const bool same = __funnelshift_r(w0, w1, sh * 8) == tail;
+    uint32_t next_state = kWalk;
+    if (!fast || same) next_state = kCheck;                        // worth a closer look
+    uint32_t ones2 = 0;
+    if (kRuns)
+    {
+      // a series of 1-hops is a run of one byte: the stretch is done in closed form (walk_stretch),
+      // except that short stretches are cheaper to walk while the in-smem filter applies
+      ones2 = hop2 == 1 ? ones + 1 : 0;
+      const bool stretch = run != 0 && ones2 >= (fast ? (uint32_t)kStretchMin : 1u);
+      if (stretch) next_state = kStretch;
+    }
+    if (ends) next_state = kFinish;
+    if (walking)
+    {
+      state = next_state;
+      if (go) { total = tot2; hop = hop2; if (kRuns) ones = ones2; }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kSearchThreads, 1)
 k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, const uint32_t* run_fwd,
          const uint16_t* ones_back, uint32_t* mlen, uint16_t* mdist, uint32_t tiles_per_block, Geom g, int use_bulk,
@@ -334,38 +377,12 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
 
     // ---- fast hops (smallz4.h:192-233, the rejecting path): follow the chain while the bytes a longer match
     // would need first differ.  A lane that meets anything else parks in a state for the slow part.
-    // Written without branches around the loads: every lane executes the same dozen instructions.
-#pragma unroll 1
-    for (uint32_t it = 0; it < fast_hops; it++)
-    {
-      const bool walking = state == kWalk;
-      const uint32_t tot2 = total + hop;
-      const bool ends = hop == 0 || tot2 > kWindow;                  // smallz4.h:192,196
-      const bool go = walking && !ends;
-      // chain entry of the candidate q = p - tot2 (at 65535 its value ends the walk either way)
-      const uint32_t hop2 = go ? lds_u16(cbase - 2 * tot2) : 0;
-      // the candidate's bytes q+len-3 .. q+len against p's: the group the reference compares first
-      // (unaligned 32-bit read from shared memory: two aligned words and a funnel shift)
-      const smem_addr a = dl - tot2;
-      const uint32_t sh = (uint32_t)(a - v.s_data) & 3u;
-      const smem_addr w = a - sh;
-      const bool peek = go && fast;
-      const uint32_t w0 = peek ? lds_u32(w) : 0, w1 = peek ? lds_u32(w + 4) : 0;
-      const bool same = __funnelshift_r(w0, w1, sh * 8) == tail;
-      const uint32_t ones2 = hop2 == 1 ? ones + 1 : 0;
-      // a series of 1-hops is a run of one byte: the stretch is done in closed form (walk_stretch),
-      // except that short stretches are cheaper to walk while the in-smem filter applies
-      const bool stretch = run != 0 && ones2 >= (fast ? (uint32_t)kStretchMin : 1u);
-      uint32_t next_state = kWalk;
-      if (!fast || same) next_state = kCheck;                        // worth a closer look
-      if (stretch) next_state = kStretch;
-      if (ends) next_state = kFinish;
-      if (walking)
-      {
-        state = next_state;
-        if (go) { total = tot2; hop = hop2; ones = ones2; }
-      }
-    }
+    // Written without branches around the loads: every lane executes the same few dozen instructions -- fewer
+    // when no walking lane of the warp is inside a byte run (no stretch bookkeeping).
+    if (__any_sync(0xffffffffu, state == kWalk && run != 0))
+      fast_hops_loop<true>(v, fast_hops, state, total, hop, ones, run, fast, tail, cbase, dl);
+    else
+      fast_hops_loop<false>(v, fast_hops, state, total, hop, ones, run, fast, tail, cbase, dl);
 
     // ---- slow part: candidates that passed the first byte, stretches, finished walks
     if (state >= kCheck)
