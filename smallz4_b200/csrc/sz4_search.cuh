@@ -211,49 +211,55 @@ __device__ __forceinline__ bool walk_stretch(const SearchView& v, const uint32_t
 }
 
 // lane states of the walk
-enum : uint32_t { kIdle = 0, kWalk = 1, kCheck = 2, kStretch = 3, kFinish = 4 };
+// kWalk: in the fast loop (the bytes a longer match needs first are staged); kSlowWalk: hops one candidate per round in the slow part
+enum : uint32_t { kIdle = 0, kWalk = 1, kCheck = 2, kStretch = 3, kFinish = 4, kSlowWalk = 5 };
 enum : uint32_t { kFastHops = 8, kStretchMin = 8 };
 
 // The rejecting path of the walk (smallz4.h:192-233) for up to `hops` candidates per lane; see k_search.
 // kRuns = false: no walking lane of the warp is inside a byte run, the stretch bookkeeping is left out.
 template <bool kRuns>
 __device__ __forceinline__ void fast_hops_loop(const SearchView& v, uint32_t hops, uint32_t& state, uint32_t& total, uint32_t& hop,
-                                               uint32_t& ones, uint32_t run, bool fast, uint32_t tail, smem_addr cbase, smem_addr dl)
+                                               uint32_t& ones, uint32_t run, uint32_t tail, smem_addr cbase, smem_addr dl)
 {
+  (void)v;
+  uint32_t w0 = 0, w1 = 0;                                         // only looked at by lanes that loaded them
 #pragma unroll 1
   for (uint32_t it = 0; it < hops; it++)
   {
-    const bool walking = state == kWalk;
     const uint32_t tot2 = total + hop;
     const bool ends = hop == 0 || tot2 > kWindow;                  // smallz4.h:192,196
+    const bool walking = state == kWalk;
     const bool go = walking && !ends;
-    // chain entry of the candidate q = p - tot2 (at 65535 its value ends the walk either way)
-    const uint32_t hop2 = go ? lds_u16(cbase - 2 * tot2) : 0;
-    // the candidate's bytes q+len-3 .. q+len against p's: the group the reference compares first
-    // (unaligned 32-bit read from shared memory: two aligned words and a funnel shift)
+    // the candidate q = p - tot2: its chain entry (at 65535 its value ends the walk either way) and its bytes
+    // q+len-3 .. q+len, the group the reference compares first with p's (an unaligned 32-bit read from shared
+    // memory: two aligned words and a funnel shift, which only looks at the low five bits of the shift)
     const smem_addr a = dl - tot2;
-    const uint32_t sh = (uint32_t)(a - v.s_data) & 3u;
-    const smem_addr w = a - sh;
-    const bool peek = go && fast;
-    const uint32_t w0 = peek ? lds_u32(w) : 0, w1 = peek ? lds_u32(w + 4) : 0;
-    const bool same = __funnelshift_r(w0, w1, sh * 8) == tail;
-    uint32_t next_state = kWalk;
-    if (!fast || same) next_state = kCheck;                        // worth a closer look
-    uint32_t ones2 = 0;
+#ifdef SZ4_EMU
+    const uint32_t lowbits = (uint32_t)(a - v.s_data);             // the staged bytes start at a multiple of 16
+#else
+    const uint32_t lowbits = a;
+#endif
+    uint32_t hop2 = hop;
+    if (go)
+    {
+      const smem_addr w = a - (lowbits & 3u);
+      hop2 = lds_u16(cbase - 2 * tot2);
+      w0 = lds_u32(w); w1 = lds_u32(w + 4);
+    }
+    const bool same = __funnelshift_r(w0, w1, lowbits * 8) == tail;
+    uint32_t next_state = same ? kCheck : kWalk;                   // kCheck: worth a closer look
     if (kRuns)
     {
       // a series of 1-hops is a run of one byte: the stretch is done in closed form (walk_stretch),
       // except that short stretches are cheaper to walk while the in-smem filter applies
-      ones2 = hop2 == 1 ? ones + 1 : 0;
-      const bool stretch = run != 0 && ones2 >= (fast ? (uint32_t)kStretchMin : 1u);
-      if (stretch) next_state = kStretch;
+      const uint32_t ones2 = hop2 == 1 ? ones + 1 : 0;
+      if (run != 0 && ones2 >= (uint32_t)kStretchMin) next_state = kStretch;
+      if (go) ones = ones2;
     }
     if (ends) next_state = kFinish;
-    if (walking)
-    {
-      state = next_state;
-      if (go) { total = tot2; hop = hop2; if (kRuns) ones = ones2; }
-    }
+    if (go) total = tot2;
+    hop = hop2;
+    if (walking) state = next_state;
   }
 }
 
@@ -363,6 +369,7 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
                 }
               }
             }
+            if (state == kWalk && !fast) state = kSlowWalk;
           }
         }
       }
@@ -380,13 +387,26 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
     // Written without branches around the loads: every lane executes the same few dozen instructions -- fewer
     // when no walking lane of the warp is inside a byte run (no stretch bookkeeping).
     if (__any_sync(0xffffffffu, state == kWalk && run != 0))
-      fast_hops_loop<true>(v, fast_hops, state, total, hop, ones, run, fast, tail, cbase, dl);
+      fast_hops_loop<true>(v, fast_hops, state, total, hop, ones, run, tail, cbase, dl);
     else
-      fast_hops_loop<false>(v, fast_hops, state, total, hop, ones, run, fast, tail, cbase, dl);
+      fast_hops_loop<false>(v, fast_hops, state, total, hop, ones, run, tail, cbase, dl);
 
     // ---- slow part: candidates that passed the first byte, stretches, finished walks
     if (state >= kCheck)
     {
+      if (state == kSlowWalk)
+      {
+        // one hop of a lane whose match reaches beyond the staged bytes: every candidate gets the closer look,
+        // and any 1-hop inside a run goes to the closed form
+        const uint32_t tot2 = total + hop;
+        if (hop == 0 || tot2 > kWindow) state = kFinish;             // smallz4.h:192,196
+        else
+        {
+          total = tot2;
+          hop = lds_u16(cbase - 2 * tot2);
+          state = (run != 0 && hop == 1) ? kStretch : kCheck;
+        }
+      }
       bool finish = state == kFinish;
       if (!finish)
       {
@@ -407,7 +427,7 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
           dl = v.s_data + (p + len - 3 - v.dlo);
           fast = len >= 4 && p + len + 1 <= v.dhi;
         }
-        state = kWalk;
+        state = fast ? kWalk : kSlowWalk;
       }
       if (finish)
       {
