@@ -224,7 +224,9 @@ __device__ __forceinline__ void fast_hops_loop(const SearchView& v, uint32_t hop
   (void)v;
   uint32_t w0 = 0, w1 = 0;                                         // only looked at by lanes that loaded them
 #pragma unroll 1
-  for (uint32_t it = 0; it < hops; it++)
+  for (uint32_t it = 0; it < hops; it += kFastHops)                // hops is rounded up to a multiple of kFastHops
+#pragma unroll
+  for (uint32_t un = 0; un < kFastHops; un++)
   {
     const uint32_t tot2 = total + hop;
     const bool ends = hop == 0 || tot2 > kWindow;                  // smallz4.h:192,196
