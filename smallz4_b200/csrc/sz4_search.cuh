@@ -213,62 +213,60 @@ __device__ __forceinline__ bool walk_stretch(const SearchView& v, const uint32_t
 // lane states of the walk
 // kWalk: in the fast loop (the bytes a longer match needs first are staged); kSlowWalk: hops one candidate per round in the slow part
 enum : uint32_t { kIdle = 0, kWalk = 1, kCheck = 2, kStretch = 3, kFinish = 4, kSlowWalk = 5 };
-enum : uint32_t { kFastHops = 8, kStretchMin = 8 };
+enum : uint32_t { kFastHops = 8 };
 
 // The rejecting path of the walk (smallz4.h:192-233) for up to `hops` candidates per lane; see k_search.
-// kRuns = false: no walking lane of the warp is inside a byte run, the stretch bookkeeping is left out.
-template <bool kRuns>
 __device__ __forceinline__ void fast_hops_loop(const SearchView& v, uint32_t hops, uint32_t& state, uint32_t& total, uint32_t& hop,
-                                               uint32_t& ones, uint32_t run, uint32_t tail, smem_addr cbase, smem_addr dl)
+                                               uint32_t run, uint32_t tail, smem_addr cbase, smem_addr dl, uint32_t min_lanes)
 {
   (void)v;
   uint32_t w0 = 0, w1 = 0;                                         // only looked at by lanes that loaded them
+  // eight hops at a time, for as long as enough lanes are still walking: the parked ones wait for the slow part
 #pragma unroll 1
-  for (uint32_t it = 0; it < hops; it += kFastHops)                // hops is rounded up to a multiple of kFastHops
-#pragma unroll
-  for (uint32_t un = 0; un < kFastHops; un++)
+  for (uint32_t it = 0; it < hops; it += kFastHops)
   {
-    const uint32_t tot2 = total + hop;
-    const bool ends = hop == 0 || tot2 > kWindow;                  // smallz4.h:192,196
-    const bool walking = state == kWalk;
-    const bool go = walking && !ends;
-    // the candidate q = p - tot2: its chain entry (at 65535 its value ends the walk either way) and its bytes
-    // q+len-3 .. q+len, the group the reference compares first with p's (an unaligned 32-bit read from shared
-    // memory: two aligned words and a funnel shift, which only looks at the low five bits of the shift)
-    const smem_addr a = dl - tot2;
+    if (it != 0 && (uint32_t)__popc(__ballot_sync(0xffffffffu, state == kWalk)) < min_lanes) break;
+    const uint32_t total_in = total;
+#pragma unroll
+    for (uint32_t un = 0; un < kFastHops; un++)
+    {
+      const uint32_t tot2 = total + hop;
+      const bool ends = hop == 0 || tot2 > kWindow;                // smallz4.h:192,196
+      const bool walking = state == kWalk;
+      const bool go = walking && !ends;
+      // the candidate q = p - tot2: its chain entry (at 65535 its value ends the walk either way) and its bytes
+      // q+len-3 .. q+len, the group the reference compares first with p's (an unaligned 32-bit read from shared
+      // memory: two aligned words and a funnel shift, which only looks at the low five bits of the shift)
+      const smem_addr a = dl - tot2;
 #ifdef SZ4_EMU
-    const uint32_t lowbits = (uint32_t)(a - v.s_data);             // the staged bytes start at a multiple of 16
+      const uint32_t lowbits = (uint32_t)(a - v.s_data);           // the staged bytes start at a multiple of 16
 #else
-    const uint32_t lowbits = a;
+      const uint32_t lowbits = a;
 #endif
-    uint32_t hop2 = hop;
-    if (go)
-    {
-      const smem_addr w = a - (lowbits & 3u);
-      hop2 = lds_u16(cbase - 2 * tot2);
-      w0 = lds_u32(w); w1 = lds_u32(w + 4);
+      uint32_t hop2 = hop;
+      if (go)
+      {
+        const smem_addr w = a - (lowbits & 3u);
+        hop2 = lds_u16(cbase - 2 * tot2);
+        w0 = lds_u32(w); w1 = lds_u32(w + 4);
+      }
+      const bool same = __funnelshift_r(w0, w1, lowbits * 8) == tail;
+      uint32_t next_state = same ? kCheck : kWalk;                 // kCheck: worth a closer look
+      if (ends) next_state = kFinish;
+      if (go) total = tot2;
+      hop = hop2;
+      if (walking) state = next_state;
     }
-    const bool same = __funnelshift_r(w0, w1, lowbits * 8) == tail;
-    uint32_t next_state = same ? kCheck : kWalk;                   // kCheck: worth a closer look
-    if (kRuns)
-    {
-      // a series of 1-hops is a run of one byte: the stretch is done in closed form (walk_stretch),
-      // except that short stretches are cheaper to walk while the in-smem filter applies
-      const uint32_t ones2 = hop2 == 1 ? ones + 1 : 0;
-      if (run != 0 && ones2 >= (uint32_t)kStretchMin) next_state = kStretch;
-      if (go) ones = ones2;
-    }
-    if (ends) next_state = kFinish;
-    if (go) total = tot2;
-    hop = hop2;
-    if (walking) state = next_state;
+    // eight hops of one position each inside a byte run, and the next one is another: a stretch, which
+    // walk_stretch does in closed form (shorter ones are cheaper to walk through the filter above)
+    if (run != 0 && state == kWalk && hop == 1 && total - total_in == kFastHops) state = kStretch;
   }
 }
 
 __global__ void __launch_bounds__(kSearchThreads, 1)
 k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, const uint32_t* run_fwd,
          const uint16_t* ones_back, uint32_t* mlen, uint16_t* mdist, uint32_t tiles_per_block, Geom g, int use_bulk,
-         uint32_t fast_hops)
+         uint32_t fast_hops, uint32_t fast_lanes)
 {
   SZ4_DYN_SMEM(smem);
   __shared__ uint64_t bar;
@@ -318,7 +316,6 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
   uint32_t tail = 0;                   // bytes p+len-3 .. p+len: the group a longer match has to reproduce first
   smem_addr cbase = v.s_pe, dl = v.s_data;   // &chain(p), &data[p + len - 3] in shared memory
   bool fast = false;                   // p + len is inside the staged bytes: candidates' bytes are too
-  uint32_t ones = 0;                   // consecutive chain entries equal to 1 seen so far
 
   // One ballot per iteration keeps `idle` (lanes that want a new position) current for all lanes.
   uint32_t idle = 0xffffffffu;
@@ -342,7 +339,7 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
           const uint32_t own = p == tw_pos ? tw_own : lds_u16(v.s_pe + 2 * (p - v.clo));
           if (own != 0)
           {
-            state = kWalk; len = 1; dist = 0; total = 0; budget = g.max_chain; tail = 0; ones = 0;
+            state = kWalk; len = 1; dist = 0; total = 0; budget = g.max_chain; tail = 0;
             hop = v.chain(p);                                        // smallz4.h:190 (absolute slot)
             run = 0;
             if (g.shift == 0) { hop = own; run = run_fwd[p]; if (run < kMinMatch) run = 0; }
@@ -360,7 +357,6 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
                 total = hop; hop = nh;
                 (void)try_candidate(v, p, p - total, stop, len, tail);
                 dist = total;
-                ones = nh == 1 ? 1u : 0u;
                 dl = v.s_data + (p + len - 3 - v.dlo);
                 fast = len >= 4 && p + len + 1 <= v.dhi;
                 if (--budget == 0 || p + len + 1 > stop)
@@ -386,12 +382,8 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
 
     // ---- fast hops (smallz4.h:192-233, the rejecting path): follow the chain while the bytes a longer match
     // would need first differ.  A lane that meets anything else parks in a state for the slow part.
-    // Written without branches around the loads: every lane executes the same few dozen instructions -- fewer
-    // when no walking lane of the warp is inside a byte run (no stretch bookkeeping).
-    if (__any_sync(0xffffffffu, state == kWalk && run != 0))
-      fast_hops_loop<true>(v, fast_hops, state, total, hop, ones, run, tail, cbase, dl);
-    else
-      fast_hops_loop<false>(v, fast_hops, state, total, hop, ones, run, tail, cbase, dl);
+    // Written without branches around the loads: every lane executes the same 17 instructions per candidate.
+    fast_hops_loop(v, fast_hops, state, total, hop, run, tail, cbase, dl, fast_lanes);
 
     // ---- slow part: candidates that passed the first byte, stretches, finished walks
     if (state >= kCheck)
@@ -416,7 +408,6 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
         if (state == kStretch)
         {
           finish = walk_stretch(v, run_fwd, ones_back, p, stop, run, total, hop, len, dist, budget, tail);
-          ones = 0;
         }
         else if (try_candidate(v, p, p - total, stop, len, tail))
         {

@@ -22,8 +22,12 @@ def main():
     ap.add_argument("kinds", nargs="*", default=["mixed", "text", "binary", "runs", "zeros", "random"])
     ap.add_argument("--size-mb", type=int, default=256)
     ap.add_argument("--level", type=int, default=9)
+    ap.add_argument("--opt", action="append", default=[], help="name=value for sz4_set_option (repeatable)")
     a = ap.parse_args()
     c = Compressor(device=0, profile=1)
+    for o in a.opt:
+        name, value = o.split("=")
+        c.set_option(name, int(value))
     c.lib.sz4_debug_counters.restype = ctypes.POINTER(ctypes.c_uint)
     c.lib.sz4_debug_counters.argtypes = [ctypes.c_void_p]
     khz = 1965e3
