@@ -405,7 +405,9 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
       if (!finish)
       {
         const uint32_t len_in = len;
-        if (state == kStretch)
+        // (a candidate that is worth a closer look and opens a stretch of its run goes to the closed form as well:
+        // inside p's own run every candidate passes the filter)
+        if (state == kStretch || (run != 0 && hop == 1))
         {
           finish = walk_stretch(v, run_fwd, ones_back, p, stop, run, total, hop, len, dist, budget, tail);
         }
