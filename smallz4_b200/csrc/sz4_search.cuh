@@ -16,10 +16,16 @@
 
 namespace sz4
 {
+#ifndef SZ4_TILE
+#define SZ4_TILE 11264
+#endif
+#ifndef SZ4_LOOK
+#define SZ4_LOOK 1024
+#endif
 enum : uint32_t
 {
-  kTile          = 8192,     // positions per CTA
-  kLook          = 3584,     // bytes staged behind the tile for match extension
+  kTile          = SZ4_TILE, // positions per CTA
+  kLook          = SZ4_LOOK, // bytes staged behind the tile for match extension
   kHist          = 65536,    // history staged in front of the tile
   kSearchThreads = 1024,
   kDataBytes     = kHist + kTile + kLook + 16,
@@ -266,7 +272,7 @@ __device__ __forceinline__ void fast_hops_loop(const SearchView& v, uint32_t hop
 __global__ void __launch_bounds__(kSearchThreads, 1)
 k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, const uint32_t* run_fwd,
          const uint16_t* ones_back, uint32_t* mlen, uint16_t* mdist, uint32_t tiles_per_block, Geom g, int use_bulk,
-         uint32_t fast_hops, uint32_t fast_lanes)
+         uint32_t fast_hops, uint32_t fast_lanes, uint32_t dense_a, uint32_t dense_b)
 {
   SZ4_DYN_SMEM(smem);
   __shared__ uint64_t bar;
@@ -296,7 +302,7 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
   __shared__ uint32_t tw_pos_s;
   if (threadIdx.x == 0)
   {
-    next_pos = t0;
+    next_pos = 0;
     uint32_t tw = 0xffffffffu;
     const uint32_t cand = block_end(g, j) - kEndNoMatch;
     if (block_len(g, j) >= kEndNoMatch && cand >= t0 && cand < t1 && is_twice_inserted(g, cand)) tw = cand;
@@ -309,13 +315,14 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
   const uint32_t tw_own = tw_pos != 0xffffffffu ? saved_pe[(tw_pos + kEndNoMatch - g.halo) / g.block_size] : 0;
 
   const uint32_t lane = threadIdx.x & 31;
+  const uint32_t tlen = t1 - t0, n_pass = dense_a != 0 ? 3u : 1u;
   uint32_t state = kIdle;
   bool exhausted = false;
   uint32_t p = 0, len = 1, dist = 0, total = 0, hop = 0, budget = 0;
   uint32_t run = 0;                    // bytes equal to data[p] from p on, when the stretch shortcut applies
   uint32_t tail = 0;                   // bytes p+len-3 .. p+len: the group a longer match has to reproduce first
   smem_addr cbase = v.s_pe, dl = v.s_data;   // &chain(p), &data[p + len - 3] in shared memory
-  bool fast = false;                   // p + len is inside the staged bytes: candidates' bytes are too
+  bool fast = false;                   // the next candidate's bytes up to q + len are inside the staged range
 
   // One ballot per iteration keeps `idle` (lanes that want a new position) current for all lanes.
   uint32_t idle = 0xffffffffu;
@@ -332,17 +339,26 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
       base = __shfl_sync(0xffffffffu, base, leader);
       if (state == kIdle && !exhausted)
       {
-        p = base + (uint32_t)__popc(idle & ((1u << lane) - 1));
-        if (p >= t1) exhausted = true;
+        // The tile is gone through three times: positions whose first two hops are short (a dense class: a long
+        // chain) first, the bulk last -- so that the longest walks do not start when the tile is nearly done.
+        const uint32_t idx = base + (uint32_t)__popc(idle & ((1u << lane) - 1));
+        const uint32_t pass = idx >= 2 * tlen ? 2u : (idx >= tlen ? 1u : 0u);
+        p = t0 + idx - pass * tlen;
+        if (idx >= n_pass * tlen) exhausted = true;
         else
         {
           const uint32_t own = p == tw_pos ? tw_own : lds_u16(v.s_pe + 2 * (p - v.clo));
-          if (own != 0)
+          uint32_t first = own != 0 ? v.chain(p) : 0;                // smallz4.h:190 (absolute slot)
+          if (g.shift == 0) first = own;
+          const uint32_t nh = first != 0 ? v.chain(p - first) : 0;
+          const uint32_t two = nh != 0 ? first + nh : 0xffffffffu;
+          const uint32_t cls = n_pass == 1 ? 0u : (two < dense_a ? 0u : (two < dense_b ? 1u : 2u));
+          if (own != 0 && cls == pass)
           {
             state = kWalk; len = 1; dist = 0; total = 0; budget = g.max_chain; tail = 0;
-            hop = v.chain(p);                                        // smallz4.h:190 (absolute slot)
+            hop = first;
             run = 0;
-            if (g.shift == 0) { hop = own; run = run_fwd[p]; if (run < kMinMatch) run = 0; }
+            if (g.shift == 0) { run = run_fwd[p]; if (run < kMinMatch) run = 0; }
             cbase = v.s_pe + 2 * (p - v.shift - v.clo);
             dl = v.s_data + (p + len - v.dlo);
             fast = false;
@@ -351,14 +367,13 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
             // it opens a stretch of a run, which walk_stretch does without touching the bytes.
             if (hop != 0)
             {
-              const uint32_t nh = v.chain(p - hop);
               if (!(run != 0 && nh == 1))
               {
                 total = hop; hop = nh;
                 (void)try_candidate(v, p, p - total, stop, len, tail);
                 dist = total;
                 dl = v.s_data + (p + len - 3 - v.dlo);
-                fast = len >= 4 && p + len + 1 <= v.dhi;
+                fast = len >= 4 && (p + len + 1 <= v.dhi || total + hop + v.dhi >= p + len + 1);
                 if (--budget == 0 || p + len + 1 > stop)
                 {
                   mlen[p] = len;
@@ -420,8 +435,10 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
         {
           if (p + len + 1 > stop) finish = true;                     // smallz4.h:205: nothing longer fits
           dl = v.s_data + (p + len - 3 - v.dlo);
-          fast = len >= 4 && p + len + 1 <= v.dhi;
         }
+        // the filter of the fast loop reads the candidate's bytes q+len-3 .. q+len from the staged range: fine when
+        // p's are staged, and otherwise for every candidate far enough back (the next one is total + hop back)
+        fast = len >= 4 && (p + len + 1 <= v.dhi || total + hop + v.dhi >= p + len + 1);
         state = fast ? kWalk : kSlowWalk;
       }
       if (finish)
