@@ -136,19 +136,39 @@ struct SearchView
 // in which case len and tail are updated.  tail = the four bytes p+len-3 .. p+len, i.e. the first group
 // the reference's backward scan compares (smallz4.h:224-225).  The caller has checked that a longer
 // match still fits (smallz4.h:205).
-__device__ __forceinline__ bool try_candidate(const SearchView& v, uint32_t p, uint32_t q, uint32_t stop, uint32_t& len, uint32_t& tail)
+// runs (may be null) = run_fwd of sz4_runs.cuh: long stretches of one byte are stepped over by their lengths
+// instead of being compared word by word (same result; without it one position at the head of a run of a few
+// hundred KiB keeps its CTA busy for milliseconds).  Only valid where candidates share p's first bytes (no dictionary).
+__device__ __forceinline__ bool try_candidate(const SearchView& v, uint32_t p, uint32_t q, uint32_t stop, uint32_t& len, uint32_t& tail,
+                                              const uint32_t* runs)
 {
   const uint32_t need = len + 1;
   if (len >= 4)
   {
     // phase 1, smallz4.h:224-233: bytes (0, need) in 4-byte groups from the top
     if (tail != v.word_at(q + len - 3)) return false;                  // first group from the top
-    for (int32_t off = (int32_t)need - 8; off > 0; off -= 4)
+    int32_t off = (int32_t)need - 8;
+    int32_t known = 0;                                                 // bytes [0, known) are the same byte on both sides
+    if (runs != nullptr && off > 64) known = (int32_t)min(min(runs[p], runs[q]), 0x7fffffffu);
+    for (; off > 0 && off + 4 > known; off -= 4)
       if (v.word_at(p + off) != v.word_at(q + off)) return false;
   }
   // phase 2, smallz4.h:236-243
-  uint32_t f = need;
-  while (p + f + 4 <= stop && v.word_at(p + f) == v.word_at(q + f)) f += 4;
+  uint32_t f = need, uniform = 0;
+  while (p + f + 4 <= stop)
+  {
+    const uint32_t w = v.word_at(p + f);
+    if (w != v.word_at(q + f)) break;
+    f += 4;
+    if (runs != nullptr && w == __funnelshift_r(w, w, 8) && ++uniform >= 16)
+    {
+      // both sides are inside runs of the byte just compared: equal for as long as the shorter one lasts
+      uint32_t s = min(runs[p + f - 1], runs[q + f - 1]) - 1;
+      s = min(s, stop - (p + f));
+      f += s;
+      uniform = 0;
+    }
+  }
   while (p + f < stop && v.byte_at(p + f) == v.byte_at(q + f)) f++;
   len = f;
   tail = v.word_at(p + f - 3);
@@ -202,7 +222,7 @@ __device__ __forceinline__ bool walk_stretch(const SearchView& v, const uint32_t
     {
       if (p + len + 1 > stop) return true;
       if (len != len_in) tail = v.word_at(p + len - 3);
-      if (try_candidate(v, p, top - kstar, stop, len, tail))
+      if (try_candidate(v, p, top - kstar, stop, len, tail, run_fwd))
       {
         dist = total + kstar;
         if (--budget == 0) return true;
@@ -316,6 +336,7 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
 
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t tlen = t1 - t0, n_pass = dense_a != 0 ? 3u : 1u;
+  const uint32_t* runs = g.shift == 0 ? run_fwd : nullptr;       // filled in only without a dictionary
   uint32_t state = kIdle;
   bool exhausted = false;
   uint32_t p = 0, len = 1, dist = 0, total = 0, hop = 0, budget = 0;
@@ -370,7 +391,7 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
               if (!(run != 0 && nh == 1))
               {
                 total = hop; hop = nh;
-                (void)try_candidate(v, p, p - total, stop, len, tail);
+                (void)try_candidate(v, p, p - total, stop, len, tail, runs);
                 dist = total;
                 dl = v.s_data + (p + len - 3 - v.dlo);
                 fast = len >= 4 && (p + len + 1 <= v.dhi || total + hop + v.dhi >= p + len + 1);
@@ -426,7 +447,7 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
         {
           finish = walk_stretch(v, run_fwd, ones_back, p, stop, run, total, hop, len, dist, budget, tail);
         }
-        else if (try_candidate(v, p, p - total, stop, len, tail))
+        else if (try_candidate(v, p, p - total, stop, len, tail, runs))
         {
           dist = total;
           if (--budget == 0) finish = true;
