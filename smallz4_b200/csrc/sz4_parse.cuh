@@ -588,7 +588,8 @@ __device__ __forceinline__ void dp_segment(const uint32_t* mlen, const uint16_t*
 // One warp per 1024 positions; lane g ends up with the values of group g and they are stored coalesced.
 __global__ void __launch_bounds__(256)
 k_dp_group_reach(const uint32_t* mlen, const uint16_t* mdist, uint32_t* group_reach, uint32_t* group_reach_nf, uint32_t* group_run_end,
-                 uint32_t* group_first, uint32_t groups_per_block, Geom g)
+                 uint32_t* group_first, uint32_t* chunk_reach, uint32_t* chunk_reach_nf, uint32_t* chunk_first,
+                 uint32_t groups_per_block, Geom g)
 {
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const uint32_t chunks_per_block = (groups_per_block + 31) / 32;
@@ -619,15 +620,100 @@ k_dp_group_reach(const uint32_t* mlen, const uint16_t* mdist, uint32_t* group_re
     const size_t at = (size_t)j * groups_per_block + grp;
     group_reach[at] = mine; group_reach_nf[at] = mine_nf; group_run_end[at] = mine_run; group_first[at] = mine_first;
   }
+  // the same over the whole chunk of 32 groups, for the two-level scans of k_dp_chunk_scan
+  const uint32_t cr = __reduce_max_sync(0xffffffffu, mine), crn = __reduce_max_sync(0xffffffffu, mine_nf);
+  const uint32_t cf = __reduce_min_sync(0xffffffffu, mine_first);
+  if (lane == 0)
+  {
+    const size_t at = (size_t)j * chunks_per_block + c;
+    chunk_reach[at] = cr; chunk_reach_nf[at] = crn; chunk_first[at] = cf;
+  }
 }
 
-// One warp per block: exclusive prefix maximum of the group reaches, 32 groups per step, and a boundary
-// wherever the segment is long enough and nothing from the left reaches more than kDpSlack beyond it.
+// One warp per block, over its chunks of 32 groups (1024 positions): chunk_reach / chunk_reach_nf become the reach of
+// everything LEFT of the chunk (exclusive prefix maximum), chunk_first the first match candidate BEHIND it (exclusive
+// suffix minimum).  128 steps of 32 chunks for a 4 MiB block.
 // (kernels that give one warp a sequential job pack four such warps into a CTA: a warp's scheduler is
 // its index in the CTA modulo 4, so single-warp CTAs would all queue on the first of the SM's four schedulers)
 __global__ void __launch_bounds__(128)
-k_dp_plan(uint32_t* group_reach, const uint32_t* group_reach_nf, const uint32_t* group_run_end, uint32_t* group_first,
-          uint32_t groups_per_block, DpTask* tasks, uint32_t* task_count, uint32_t max_seg, Geom g)
+k_dp_chunk_scan(uint32_t* chunk_reach, uint32_t* chunk_reach_nf, uint32_t* chunk_first, uint32_t chunks_per_block, Geom g)
+{
+  const uint32_t j = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (j >= g.n_blocks) return;
+  const uint32_t lane = threadIdx.x & 31;
+  uint32_t* cr = chunk_reach + (size_t)j * chunks_per_block;
+  uint32_t* cn = chunk_reach_nf + (size_t)j * chunks_per_block;
+  uint32_t* cf = chunk_first + (size_t)j * chunks_per_block;
+  uint32_t carry = 0, carry_nf = 0;
+#pragma unroll 2
+  for (uint32_t c0 = 0; c0 < chunks_per_block; c0 += 32)
+  {
+    const bool in = c0 + lane < chunks_per_block;
+    uint32_t incl = in ? cr[c0 + lane] : 0, incl_nf = in ? cn[c0 + lane] : 0;
+#pragma unroll
+    for (uint32_t d = 1; d < 32; d <<= 1)
+    {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d), tn = __shfl_up_sync(0xffffffffu, incl_nf, d);
+      if (lane >= d) { incl = max(incl, t); incl_nf = max(incl_nf, tn); }
+    }
+    uint32_t before = __shfl_up_sync(0xffffffffu, incl, 1), before_nf = __shfl_up_sync(0xffffffffu, incl_nf, 1);
+    before = lane == 0 ? carry : max(before, carry);
+    before_nf = lane == 0 ? carry_nf : max(before_nf, carry_nf);
+    if (in) { cr[c0 + lane] = before; cn[c0 + lane] = before_nf; }
+    carry = max(carry, __shfl_sync(0xffffffffu, incl, 31));
+    carry_nf = max(carry_nf, __shfl_sync(0xffffffffu, incl_nf, 31));
+  }
+  uint32_t behind = 0xffffffffu;
+#pragma unroll 2
+  for (int32_t c0 = (int32_t)((chunks_per_block - 1) & ~31u); c0 >= 0; c0 -= 32)
+  {
+    const bool in = (uint32_t)c0 + lane < chunks_per_block;
+    uint32_t f = in ? cf[(uint32_t)c0 + lane] : 0xffffffffu;
+#pragma unroll
+    for (uint32_t d = 1; d < 32; d <<= 1)
+    {
+      const uint32_t t = __shfl_down_sync(0xffffffffu, f, d);
+      if (lane + d < 32) f = min(f, t);
+    }
+    uint32_t after = __shfl_down_sync(0xffffffffu, f, 1);
+    after = lane == 31 ? behind : min(after, behind);
+    if (in) cf[(uint32_t)c0 + lane] = after;
+    behind = min(behind, __shfl_sync(0xffffffffu, f, 0));
+  }
+}
+
+// One warp per chunk: reach_before[g] = largest position + length over everything left of group g (the redo of
+// k_dp_verify stops early with it).
+__global__ void __launch_bounds__(256)
+k_dp_reach_before(const uint32_t* group_reach, const uint32_t* chunk_reach, uint32_t* reach_before, uint32_t groups_per_block, Geom g)
+{
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const uint32_t chunks_per_block = groups_per_block / 32;
+  if (warp >= g.n_blocks * chunks_per_block) return;
+  const size_t at = (size_t)warp * 32 + lane;                  // = block * groups_per_block + chunk * 32 + lane
+  uint32_t incl = group_reach[at];
+#pragma unroll
+  for (uint32_t d = 1; d < 32; d <<= 1)
+  {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl = max(incl, t);
+  }
+  uint32_t before = __shfl_up_sync(0xffffffffu, incl, 1);
+  const uint32_t carry = chunk_reach[warp];
+  reach_before[at] = lane == 0 ? carry : max(before, carry);
+}
+
+// One warp per block picks the segment boundaries: the first group at least kDpSeg behind the previous boundary
+// where nothing from the left reaches more than kDpSlack beyond it -- or that lies inside a long run of unpriced
+// matches, see DpTask.  Only the chunks it looks at are evaluated (a boundary is usually found in the first one).
+struct DpPlanIn
+{
+  const uint32_t* group_reach; const uint32_t* group_reach_nf; const uint32_t* group_run_end; const uint32_t* group_first;
+  const uint32_t* chunk_reach; const uint32_t* chunk_reach_nf; const uint32_t* chunk_first;      // after k_dp_chunk_scan
+};
+
+__global__ void __launch_bounds__(128)
+k_dp_plan(DpPlanIn in, uint32_t groups_per_block, DpTask* tasks, uint32_t* task_count, uint32_t max_seg, Geom g)
 {
   const uint32_t j = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (j >= g.n_blocks) return;
@@ -635,87 +721,65 @@ k_dp_plan(uint32_t* group_reach, const uint32_t* group_reach_nf, const uint32_t*
   const uint32_t lane = threadIdx.x & 31;
   DpTask* out = tasks + (size_t)j * max_seg;
   if (n <= kEndNoMatch) { if (lane == 0) task_count[j] = 0; return; }     // smallz4.h:755
-  uint32_t* gr = group_reach + (size_t)j * groups_per_block;   // in: reach of each group; out: reach of everything left of it
-  const uint32_t* gn = group_reach_nf + (size_t)j * groups_per_block;
-  const uint32_t* ge = group_run_end + (size_t)j * groups_per_block;
-  uint32_t* gf = group_first + (size_t)j * groups_per_block;   // in: first candidate of each group; out: first one at or behind it
+  const uint32_t chunks_per_block = groups_per_block / 32;
+  const uint32_t* gr = in.group_reach + (size_t)j * groups_per_block;
+  const uint32_t* gn = in.group_reach_nf + (size_t)j * groups_per_block;
+  const uint32_t* ge = in.group_run_end + (size_t)j * groups_per_block;
+  const uint32_t* gf = in.group_first + (size_t)j * groups_per_block;
+  const uint32_t* cr = in.chunk_reach + (size_t)j * chunks_per_block;
+  const uint32_t* cn = in.chunk_reach_nf + (size_t)j * chunks_per_block;
+  const uint32_t* cf = in.chunk_first + (size_t)j * chunks_per_block;
   const uint32_t groups = (n + 31) / 32;
+  uint32_t count = 0, last = 0;
+  uint32_t gq = kDpSeg / 32;                                     // first group that may carry the next boundary
+  while (gq < groups && count + 2 < max_seg)
   {
-    uint32_t behind = 0xffffffffu;
-    for (int32_t g0 = (int32_t)((groups - 1) & ~31u); g0 >= 0; g0 -= 32)
-    {
-      uint32_t f = (uint32_t)g0 + lane < groups ? gf[(uint32_t)g0 + lane] : 0xffffffffu;
-#pragma unroll
-      for (uint32_t d = 1; d < 32; d <<= 1)
-      {
-        const uint32_t t = __shfl_down_sync(0xffffffffu, f, d);
-        if (lane + d < 32) f = min(f, t);
-      }
-      f = min(f, behind);
-      if ((uint32_t)g0 + lane < groups) gf[(uint32_t)g0 + lane] = f;
-      behind = __shfl_sync(0xffffffffu, f, 0);
-    }
-    __syncwarp();
-  }
-  uint32_t count = 0, last = 0, carry = 0, carry_nf = 0;
-  uint32_t nxt = lane < groups ? gr[lane] : 0, nxt_nf = lane < groups ? gn[lane] : 0;
-  for (uint32_t g0 = 0; g0 < groups; g0 += 32)
-  {
-    const uint32_t mine = nxt, mine_nf = nxt_nf;
-    if (g0 + 32 + lane < groups) { nxt = gr[g0 + 32 + lane]; nxt_nf = gn[g0 + 32 + lane]; } else { nxt = 0; nxt_nf = 0; }
-    // inclusive prefix max over the 32 groups, then shift by one lane: reach of everything left of group g0+lane
-    uint32_t incl = mine, incl_nf = mine_nf;
+    const uint32_t c = gq / 32, gi = c * 32 + lane;
+    // reach of everything left of group gi: the chunk's carry and the groups of the chunk in front of it
+    uint32_t incl = gr[gi], incl_nf = gn[gi];
 #pragma unroll
     for (uint32_t d = 1; d < 32; d <<= 1)
     {
-      uint32_t t = __shfl_up_sync(0xffffffffu, incl, d), tn = __shfl_up_sync(0xffffffffu, incl_nf, d);
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d), tn = __shfl_up_sync(0xffffffffu, incl_nf, d);
       if (lane >= d) { incl = max(incl, t); incl_nf = max(incl_nf, tn); }
     }
     uint32_t before = __shfl_up_sync(0xffffffffu, incl, 1), before_nf = __shfl_up_sync(0xffffffffu, incl_nf, 1);
+    const uint32_t carry = cr[c], carry_nf = cn[c];
     before = lane == 0 ? carry : max(before, carry);
     before_nf = lane == 0 ? carry_nf : max(before_nf, carry_nf);
-    if (g0 + lane < groups) gr[g0 + lane] = before;
-    const uint32_t x0 = (g0 + lane) * 32;
-    const bool inside = g0 + lane < groups && x0 > 0 && x0 + 64 <= n;
+    const uint32_t x0 = gi * 32;
+    const bool inside = gi >= gq && gi < groups && x0 + 64 <= n;
     const bool fits = inside && before <= x0 + kDpSlack;
     // ... or the boundary lies inside a long run of unpriced matches that all end at the same place, its whole
     // warm-up zone does too, and nothing else reaches across
     uint32_t run_end = 0;
-    if (inside && !fits && before_nf <= x0 + kDpSlack && g0 + lane + kDpWarm / 32 + 1 < groups)
+    if (inside && !fits && before_nf <= x0 + kDpSlack && gi + kDpWarm / 32 + 1 < groups)
     {
-      const uint32_t e = ge[g0 + lane];
-      if (e != 0 && ge[g0 + lane + kDpWarm / 32 + 1] == e) run_end = e;
+      const uint32_t e = ge[gi];
+      if (e != 0 && ge[gi + kDpWarm / 32 + 1] == e) run_end = e;
     }
-    // at most a few boundaries per 1024 positions: take them in order
-    uint32_t cand = __ballot_sync(0xffffffffu, fits || run_end != 0);
-    while (cand)
+    const uint32_t cand = __ballot_sync(0xffffffffu, fits || run_end != 0);
+    if (cand == 0) { gq = c * 32 + 32; continue; }
+    const int l = __ffs((int)cand) - 1;
+    const uint32_t xb = (c * 32 + (uint32_t)l) * 32;
+    const uint32_t e = __shfl_sync(0xffffffffu, run_end, l);
+    const uint32_t reach = __shfl_sync(0xffffffffu, e != 0 ? before_nf : before, l);
+    // literal counter at the top of the warm-up zone when no match candidate is near (see DpTask)
+    uint32_t ub = 0;
+    const uint32_t top = xb + kDpWarm;
+    if (e == 0 && top + 64 <= n)
     {
-      const int l = __ffs((int)cand) - 1;
-      const uint32_t xb = (g0 + (uint32_t)l) * 32;
-      cand &= cand - 1;
-      if (xb - last >= kDpSeg && count + 2 < max_seg)
-      {
-        const uint32_t e = __shfl_sync(0xffffffffu, run_end, l);
-        const uint32_t reach = __shfl_sync(0xffffffffu, e != 0 ? before_nf : before, l);
-        if (lane == 0)
-        {
-          // literal counter at the top of the warm-up zone when no match candidate is near (see DpTask)
-          uint32_t ub = 0;
-          const uint32_t top = xb + kDpWarm;
-          if (e == 0 && top + 64 <= n)
-          {
-            const uint32_t c = gf[top / 32];
-            if (c == 0xffffffffu) ub = until_bump_after(15 - kEndLiterals, n - kEndLiterals - top);
-            else if (c - top >= 64) ub = until_bump_after(15, c - top);
-          }
-          DpTask t; t.lo = last; t.hi = xb; t.reach = reach; t.aux = e | (ub << 24); out[count] = t;
-        }
-        count++;
-        last = xb;
-      }
+      // first candidate at or behind `top`: the rest of its chunk, then everything behind the chunk
+      const uint32_t tg = top / 32, tc = tg / 32;
+      uint32_t f = tc * 32 + lane >= tg ? gf[tc * 32 + lane] : 0xffffffffu;
+      f = min(__reduce_min_sync(0xffffffffu, f), cf[tc]);
+      if (f == 0xffffffffu) ub = until_bump_after(15 - kEndLiterals, n - kEndLiterals - top);
+      else if (f - top >= 64) ub = until_bump_after(15, f - top);
     }
-    carry = max(carry, __shfl_sync(0xffffffffu, incl, 31));
-    carry_nf = max(carry_nf, __shfl_sync(0xffffffffu, incl_nf, 31));
+    if (lane == 0) { DpTask t; t.lo = last; t.hi = xb; t.reach = reach; t.aux = e | (ub << 24); out[count] = t; }
+    count++;
+    last = xb;
+    gq = (xb + kDpSeg) / 32;
   }
   if (lane == 0) { DpTask t; t.lo = last; t.hi = n; t.reach = n; t.aux = 0; out[count] = t; task_count[j] = count + 1; }
 }

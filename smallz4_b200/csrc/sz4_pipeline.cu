@@ -289,21 +289,31 @@ static int run_batch(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
     // positions the DP does not price (the last five of a block, blocks of <= 12 bytes) keep what was found
     CK(cudaMemcpyAsync(mfin, mlen, (size_t)N * 4, cudaMemcpyDeviceToDevice, ctx->stream));
     const uint32_t groups_per_block = g.block_size / 32;
-    const size_t n_groups = (size_t)g.n_blocks * groups_per_block;
-    RSV(dp_reach, 4 * (n_groups * 4 + 64));
+    const size_t n_groups = (size_t)g.n_blocks * groups_per_block, n_chunks = n_groups / 32;
+    RSV(dp_reach, 5 * (n_groups * 4 + 64) + 3 * (n_chunks * 4 + 64));
     uint32_t* reach_all = (uint32_t*)ctx->dp_reach.p;
     uint32_t* reach_nf = reach_all + n_groups + 16;
     uint32_t* run_ends = reach_nf + n_groups + 16;
     uint32_t* first_cand = run_ends + n_groups + 16;
-    LAUNCH(ctx, k_dp_group_reach, div_up((uint64_t)g.n_blocks * div_up(groups_per_block, 32) * 32, 256), 256, 0,
-           (const uint32_t*)mlen, (const uint16_t*)mdist, reach_all, reach_nf, run_ends, first_cand, groups_per_block, g);
-    LAUNCH(ctx, k_dp_plan, div_up(g.n_blocks, 4), 128, 0, reach_all, (const uint32_t*)reach_nf, (const uint32_t*)run_ends, first_cand,
-           groups_per_block, (DpTask*)ctx->dp_tasks.p, (uint32_t*)ctx->dp_count.p, max_seg, g);
+    uint32_t* reach_before = first_cand + n_groups + 16;
+    uint32_t* c_reach = reach_before + n_groups + 16;
+    uint32_t* c_reach_nf = c_reach + n_chunks + 16;
+    uint32_t* c_first = c_reach_nf + n_chunks + 16;
+    LAUNCH(ctx, k_dp_group_reach, div_up((uint64_t)n_chunks * 32, 256), 256, 0, (const uint32_t*)mlen, (const uint16_t*)mdist,
+           reach_all, reach_nf, run_ends, first_cand, c_reach, c_reach_nf, c_first, groups_per_block, g);
+    LAUNCH(ctx, k_dp_chunk_scan, div_up(g.n_blocks, 4), 128, 0, c_reach, c_reach_nf, c_first, groups_per_block / 32, g);
+    LAUNCH(ctx, k_dp_reach_before, div_up((uint64_t)n_chunks * 32, 256), 256, 0, (const uint32_t*)reach_all, (const uint32_t*)c_reach,
+           reach_before, groups_per_block, g);
+    DpPlanIn plan_in;
+    plan_in.group_reach = reach_all; plan_in.group_reach_nf = reach_nf; plan_in.group_run_end = run_ends; plan_in.group_first = first_cand;
+    plan_in.chunk_reach = c_reach; plan_in.chunk_reach_nf = c_reach_nf; plan_in.chunk_first = c_first;
+    LAUNCH(ctx, k_dp_plan, div_up(g.n_blocks, 4), 128, 0, plan_in, groups_per_block, (DpTask*)ctx->dp_tasks.p, (uint32_t*)ctx->dp_count.p,
+           max_seg, g);
     LAUNCH(ctx, k_dp_spec, n_tasks, 32, kDpSmemSpec, (const uint32_t*)mlen, (const uint16_t*)mdist, mfin, dp, (const DpTask*)ctx->dp_tasks.p,
            (const uint32_t*)ctx->dp_count.p, (DpState*)ctx->dp_states.p, (uint32_t*)ctx->dp_overlays.p, max_seg, (uint32_t*)ctx->dp_redo.p, g);
     LAUNCH(ctx, k_dp_verify, div_up(g.n_blocks, 4), 128, 4 * kDpSmem, (const uint32_t*)mlen, (const uint16_t*)mdist, mfin, dp, (const DpTask*)ctx->dp_tasks.p,
            (const uint32_t*)ctx->dp_count.p, (DpState*)ctx->dp_states.p, (uint32_t*)ctx->dp_overlays.p, max_seg,
-           (uint32_t*)ctx->dp_redo.p, ctx->debug_keep == 0, (const uint32_t*)ctx->dp_reach.p, groups_per_block, g);
+           (uint32_t*)ctx->dp_redo.p, ctx->debug_keep == 0, (const uint32_t*)reach_before, groups_per_block, g);
     if (ctx->debug_keep)
       LAUNCH(ctx, k_dp_cost_fix, n_tasks, 256, 0, dp, (const DpTask*)ctx->dp_tasks.p, (const uint32_t*)ctx->dp_count.p,
              (const DpState*)ctx->dp_states.p, max_seg, g);
