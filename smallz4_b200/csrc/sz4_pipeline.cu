@@ -55,7 +55,6 @@ struct sz4_ctx
   int      force_scalar = 0;
   uint32_t fast_hops = 32;     // k_search: at most this many candidates per lane and round in the fast loop ...
   uint32_t dense_a = 256, dense_b = 2048;   // k_search: first-two-hops distance below which a position goes in the first / second pass (0 = one pass)
-  uint32_t hints = 1;          // k_search: start walks from the left neighbour's match (level 9 without a dictionary)
   uint32_t fast_lanes = 8;     // ... which goes on in steps of eight while at least this many lanes are still walking
   // device memory (grow-only)
   DevBuf data, ph, pe, mlen, mdist, scratch, hist, hist_scanned, partials, seqs, seq_count, packed,
@@ -237,7 +236,7 @@ static int run_batch(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
       }
       LAUNCH(ctx, k_search, g.n_blocks * tiles_per_block, kSearchThreads, kSearchSmem, (const uint8_t*)data, (const uint16_t*)pe,
              (const uint32_t*)saved_pe, (const uint32_t*)ctx->run_fwd.p, (const uint16_t*)ctx->ones_back.p, mlen, mdist,
-             tiles_per_block, g, ctx->stage_bulk, ctx->fast_hops, ctx->fast_lanes, ctx->dense_a, ctx->dense_b, ctx->hints);
+             tiles_per_block, g, ctx->stage_bulk, ctx->fast_hops, ctx->fast_lanes, ctx->dense_a, ctx->dense_b);
       PHASE(3);
       if (g.max_chain <= kLazyMax)
         LAUNCH(ctx, k_greedy_filter, div_up(g.n_blocks, 4), 128, 0, (const uint8_t*)data, (const uint16_t*)pe, (const uint32_t*)saved_pe, mlen, mdist, g);
@@ -555,7 +554,6 @@ int sz4_set_option(sz4_ctx* ctx, const char* name, long long value)
   if (!strcmp(name, "fast_hops")) { if (value < 1 || value > 64) return SZ4_ERR_ARG; ctx->fast_hops = (uint32_t)value; return SZ4_OK; }
   if (!strcmp(name, "dense_a")) { if (value < 0 || value > 65536) return SZ4_ERR_ARG; ctx->dense_a = (uint32_t)value; return SZ4_OK; }
   if (!strcmp(name, "dense_b")) { if (value < 0 || value > 65536) return SZ4_ERR_ARG; ctx->dense_b = (uint32_t)value; return SZ4_OK; }
-  if (!strcmp(name, "hints")) { ctx->hints = value != 0; return SZ4_OK; }
   if (!strcmp(name, "fast_lanes")) { if (value < 0 || value > 32) return SZ4_ERR_ARG; ctx->fast_lanes = (uint32_t)value; return SZ4_OK; }
   if (!strcmp(name, "profile")) { ctx->profile = value != 0; return SZ4_OK; }
   if (!strcmp(name, "force_scalar")) { ctx->force_scalar = value != 0; return SZ4_OK; }

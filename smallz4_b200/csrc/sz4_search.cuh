@@ -292,7 +292,7 @@ __device__ __forceinline__ void fast_hops_loop(const SearchView& v, uint32_t hop
 __global__ void __launch_bounds__(kSearchThreads, 1)
 k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, const uint32_t* run_fwd,
          const uint16_t* ones_back, uint32_t* mlen, uint16_t* mdist, uint32_t tiles_per_block, Geom g, int use_bulk,
-         uint32_t fast_hops, uint32_t fast_lanes, uint32_t dense_a, uint32_t dense_b, uint32_t use_hints)
+         uint32_t fast_hops, uint32_t fast_lanes, uint32_t dense_a, uint32_t dense_b)
 {
   SZ4_DYN_SMEM(smem);
   __shared__ uint64_t bar;
@@ -337,8 +337,6 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t tlen = t1 - t0, n_pass = dense_a != 0 ? 3u : 1u;
   const uint32_t* runs = g.shift == 0 ? run_fwd : nullptr;       // filled in only without a dictionary
-  // hints need the walk to end only at the end of the chain (no budget of improvements) and an undisturbed ring
-  const bool hints = use_hints != 0 && g.shift == 0 && g.max_chain >= kWindow;
   uint32_t state = kIdle;
   bool exhausted = false;
   uint32_t p = 0, len = 1, dist = 0, total = 0, hop = 0, budget = 0;
@@ -346,7 +344,6 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
   uint32_t tail = 0;                   // bytes p+len-3 .. p+len: the group a longer match has to reproduce first
   smem_addr cbase = v.s_pe, dl = v.s_data;   // &chain(p), &data[p + len - 3] in shared memory
   bool fast = false;                   // the next candidate's bytes up to q + len are inside the staged range
-  bool hinted = false;                 // the walk started from the left neighbour's match instead of from nothing
 
   // One ballot per iteration keeps `idle` (lanes that want a new position) current for all lanes.
   uint32_t idle = 0xffffffffu;
@@ -363,26 +360,12 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
       base = __shfl_sync(0xffffffffu, base, leader);
       if (state == kIdle && !exhausted)
       {
+        // The tile is gone through three times: positions whose first two hops are short (a dense class: a long
+        // chain) first, the bulk last -- so that the longest walks do not start when the tile is nearly done.
         const uint32_t idx = base + (uint32_t)__popc(idle & ((1u << lane) - 1));
-        uint32_t pass = 0;
-        p = t0 + idx;
-        if (hints)
-        {
-          // The tile is gone through three times: positions 0, 4, 8, ... first, then 2, 6, 10, ..., then the odd ones.
-          // A position of the later rounds usually finds the final match of its left neighbour in HBM already, and
-          // that match, one or two bytes shorter, is a match of its own: see `hinted` below.
-          const uint32_t na = (tlen + 3) / 4, nb = (tlen + 1) / 4;   // positions 0 mod 4, 2 mod 4
-          pass = idx >= na + nb ? 2u : (idx >= na ? 1u : 0u);
-          p = t0 + (pass == 0 ? 4 * idx : (pass == 1 ? 4 * (idx - na) + 2 : 2 * (idx - na - nb) + 1));
-        }
-        else if (n_pass == 3)
-        {
-          // The tile is gone through three times: positions whose first two hops are short (a dense class: a long
-          // chain) first, the bulk last -- so that the longest walks do not start when the tile is nearly done.
-          pass = idx >= 2 * tlen ? 2u : (idx >= tlen ? 1u : 0u);
-          p = t0 + idx - pass * tlen;
-        }
-        if (idx >= (hints ? tlen : n_pass * tlen)) exhausted = true;
+        const uint32_t pass = idx >= 2 * tlen ? 2u : (idx >= tlen ? 1u : 0u);
+        p = t0 + idx - pass * tlen;
+        if (idx >= n_pass * tlen) exhausted = true;
         else
         {
           const uint32_t own = p == tw_pos ? tw_own : lds_u16(v.s_pe + 2 * (p - v.clo));
@@ -390,7 +373,7 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
           if (g.shift == 0) first = own;
           const uint32_t nh = first != 0 ? v.chain(p - first) : 0;
           const uint32_t two = nh != 0 ? first + nh : 0xffffffffu;
-          const uint32_t cls = (hints || n_pass == 1) ? pass : (two < dense_a ? 0u : (two < dense_b ? 1u : 2u));
+          const uint32_t cls = n_pass == 1 ? 0u : (two < dense_a ? 0u : (two < dense_b ? 1u : 2u));
           if (own != 0 && cls == pass)
           {
             state = kWalk; len = 1; dist = 0; total = 0; budget = g.max_chain; tail = 0;
@@ -400,29 +383,10 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
             cbase = v.s_pe + 2 * (p - v.shift - v.clo);
             dl = v.s_data + (p + len - v.dlo);
             fast = false;
-            hinted = false;
-            if (hints && pass != 0 && run == 0 && p >= t0 + 2)
-            {
-              // The neighbour's match {L, d} makes {L - 1 or L - 2, d} a match of p, so the longest one of p is at
-              // least that long and the walk may skip everything shorter: it starts as if a match of one byte less
-              // had been found.  The result is the same -- the nearest candidate of the greatest length -- as long
-              // as the walk finds a match at all; if it does not (the neighbour's candidate is not on p's chain:
-              // block borders, DESIGN.md Q-twice), the position is walked again the plain way.
-              const uint32_t back = pass == 1 ? 2u : 1u;
-              const uint32_t nl = __ldcg(mlen + p - back);
-              if (nl >= back + 6)
-              {
-                hinted = true;
-                len = nl - back - 1;
-                tail = v.word_at(p + len - 3);
-                dl = v.s_data + (p + len - 3 - v.dlo);
-                fast = p + len + 1 <= v.dhi || hop + v.dhi >= p + len + 1;
-              }
-            }
             // The first candidate is accepted unseen (smallz4.h:224-233 compare nothing while the best
             // length is 1), so it is handled right here instead of costing the lane a round -- unless
             // it opens a stretch of a run, which walk_stretch does without touching the bytes.
-            if (hop != 0 && !hinted)
+            if (hop != 0)
             {
               if (!(run != 0 && nh == 1))
               {
@@ -497,21 +461,6 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
         // p's are staged, and otherwise for every candidate far enough back (the next one is total + hop back)
         fast = len >= 4 && (p + len + 1 <= v.dhi || total + hop + v.dhi >= p + len + 1);
         state = fast ? kWalk : kSlowWalk;
-      }
-      if (finish && hinted && dist == 0)
-      {
-        // nothing as long as the neighbour promised is on this chain: walk it again without the hint
-        // (the first candidate is accepted unseen, as in the refill above; hinted positions are not inside runs)
-        hinted = false; finish = false;
-        len = 1; budget = g.max_chain; tail = 0;
-        total = p == tw_pos ? tw_own : lds_u16(v.s_pe + 2 * (p - v.clo));
-        hop = v.chain(p - total);
-        (void)try_candidate(v, p, p - total, stop, len, tail, runs);
-        dist = total;
-        dl = v.s_data + (p + len - 3 - v.dlo);
-        fast = len >= 4 && (p + len + 1 <= v.dhi || total + hop + v.dhi >= p + len + 1);
-        state = fast ? kWalk : kSlowWalk;
-        if (--budget == 0 || p + len + 1 > stop) finish = true;
       }
       if (finish)
       {
