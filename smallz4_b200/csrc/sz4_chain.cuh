@@ -19,7 +19,17 @@
 
 namespace sz4
 {
-// sorted[r] = (hash << 32) | position, ascending hash then position.
+// sorted[r] = (four bytes << 32) | position, ascending hash20 of the bytes, then position.
+// previousHash entry of position p whose predecessor in its hash class is q (smallz4.h:659-676, 783-795)
+__device__ __forceinline__ uint32_t hash_link(const Geom& g, uint32_t p, uint32_t q)
+{
+  uint32_t d = p - q;
+  if (d > kWindow) d = 0;                                                     // smallz4.h:668
+  else if (g.legacy && (q - g.halo) / g.block_size != (p - g.halo) / g.block_size) d = 0;
+  return d;
+}
+
+// previousHash only (the dictionary path, whose shifted ring k_exact_walk below replays from the flat array)
 __global__ void __launch_bounds__(256)
 k_link(const uint64_t* sorted, uint32_t n, uint16_t* ph, Geom g)
 {
@@ -31,15 +41,44 @@ k_link(const uint64_t* sorted, uint32_t n, uint16_t* ph, Geom g)
   if (r > 0)
   {
     uint64_t e0 = sorted[r - 1];
-    if ((e0 >> 32) == (e >> 32))
-    {
-      uint32_t q = (uint32_t)e0;
-      d = p - q;
-      if (d > kWindow) d = 0;                                                   // smallz4.h:668
-      else if (g.legacy && (q - g.halo) / g.block_size != (p - g.halo) / g.block_size) d = 0;   // smallz4.h:783-795
-    }
+    if (hash20((uint32_t)(e0 >> 32)) == hash20((uint32_t)(e >> 32))) d = hash_link(g, p, (uint32_t)e0);
   }
   ph[p] = (uint16_t)d;
+}
+
+// previousExact straight from the sorted array (no dictionary): the elements in front of r with the same hash ARE
+// the hash chain of position p (smallz4.h:681-720 follows previousHash from p), nearest first, and they carry
+// their four bytes.  Same stops as k_exact_walk: a link longer than 65535 or across a legacy block, the sum of
+// the links beyond 65535, the walk leaving what the reference could look at (floor_of), and a chain member whose
+// ring entry the next block's lookback has zeroed (Q-twice).  One coalesced read per chain member instead of a
+// 2-byte and a 4-byte random read; previousHash itself is never stored.
+__global__ void __launch_bounds__(256)
+k_chain(const uint64_t* sorted, uint32_t n, uint16_t* pe, Geom g)
+{
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const uint64_t e = sorted[r];
+  const uint32_t p = (uint32_t)e, four = (uint32_t)(e >> 32), h = hash20(four);
+  const uint32_t floor_pos = floor_of(g, p);
+  uint32_t result = 0, total = 0, at = p;
+  for (uint32_t k = r; k > 0; )
+  {
+    k--;
+    const uint64_t e0 = sorted[k];
+    const uint32_t w = (uint32_t)(e0 >> 32), q = (uint32_t)e0;
+    if (hash20(w) != h) break;                                 // front of the hash class
+    // the link at -> q is `at`'s ring entry: zero for a position the next block has inserted again (its own walk,
+    // at == p, still saw the value: k_twice_save / own_entry)
+    const uint32_t step = (at != p && is_twice_inserted(g, at)) ? 0u : hash_link(g, at, q);
+    if (step == 0) break;
+    total += step;
+    if (total > kWindow) break;
+    if (q < floor_pos) break;                                  // in front of the reference's buffer (UB-1): "no match"
+    if (w == four) { result = total; break; }
+    if (total == kWindow) break;
+    at = q;
+  }
+  pe[p] = (uint16_t)result;
 }
 
 // one thread per block border k: position halo + k*block_size - 12

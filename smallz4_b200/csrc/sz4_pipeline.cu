@@ -202,9 +202,15 @@ static int run_batch(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
         dst = (dst == bufA) ? bufB : bufA;
       }
       PHASE(1);
-      LAUNCH(ctx, k_link, div_up(count, 256), 256, 0, (const uint64_t*)src, count, ph, g);
-      LAUNCH(ctx, k_twice_save, div_up(g.n_blocks, 64), 64, 0, ph, saved_ph, g);
-      LAUNCH(ctx, k_exact_walk, div_up(count, 256), 256, 0, (const uint8_t*)data, (const uint16_t*)ph, (const uint32_t*)saved_ph, pe, first, count, g);
+      if (g.shift == 0)
+        LAUNCH(ctx, k_chain, div_up(count, 256), 256, 0, (const uint64_t*)src, count, pe, g);
+      else
+      {
+        // with a dictionary the ring is read one slot off (DESIGN.md Q-dict): previousHash as a flat array, then the walk
+        LAUNCH(ctx, k_link, div_up(count, 256), 256, 0, (const uint64_t*)src, count, ph, g);
+        LAUNCH(ctx, k_twice_save, div_up(g.n_blocks, 64), 64, 0, ph, saved_ph, g);
+        LAUNCH(ctx, k_exact_walk, div_up(count, 256), 256, 0, (const uint8_t*)data, (const uint16_t*)ph, (const uint32_t*)saved_ph, pe, first, count, g);
+      }
       LAUNCH(ctx, k_twice_save, div_up(g.n_blocks, 64), 64, 0, pe, saved_pe, g);
 
       PHASE(2);

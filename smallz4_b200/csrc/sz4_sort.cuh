@@ -1,4 +1,4 @@
-// sz4_sort.cuh -- stable LSD radix sort of (hash20, position) pairs and a generic exclusive scan.
+// sz4_sort.cuh -- stable LSD radix sort of (four bytes, position) pairs by hash20 and a generic exclusive scan.
 //
 // Phase 1 of the per-block loop (smallz4.h:645-676: lastHash / previousHash) asks, for every
 // position, for the most recent earlier position with the same 20-bit hash.  The reference gets
@@ -115,14 +115,16 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_apply(const uint32_t* in,
 }
 
 // ------------------------------------------------------------------ radix sort passes
-// element = (hash20 << 32) | position.  Pass 0 builds the elements from the data.
+// element = (the four bytes at the position << 32) | position, sorted by hash20 of the four bytes (smallz4.h:164):
+// the words ride along so that the exact chains (sz4_chain.cuh) never have to read the data.  Pass 0 builds the
+// elements from the data.
 template <bool kFromData>
 __device__ __forceinline__ uint64_t sort_load(const uint64_t* in, const uint8_t* data, uint32_t first, uint32_t i)
 {
   if (kFromData)
   {
     uint32_t p = first + i;
-    return ((uint64_t)hash20(ld32u(data + p)) << 32) | p;
+    return ((uint64_t)ld32u(data + p) << 32) | p;
   }
   return in[i];
 }
@@ -143,7 +145,7 @@ k_sort_hist(const uint64_t* in, const uint8_t* data, uint32_t first, uint32_t n,
     if (i < n)
     {
       uint64_t e = sort_load<kFromData>(in, data, first, i);
-      atomicAdd(&h[((uint32_t)(e >> 32) >> shift) & mask], 1u);
+      atomicAdd(&h[(hash20((uint32_t)(e >> 32)) >> shift) & mask], 1u);
     }
   }
   __syncthreads();
@@ -172,7 +174,7 @@ k_sort_scatter(const uint64_t* in, uint64_t* out, const uint8_t* data, uint32_t 
     uint32_t i = base + r * 32 + lane;
     bool valid = i < n;
     elem[r] = valid ? sort_load<kFromData>(in, data, first, i) : 0;
-    uint32_t digit = valid ? (((uint32_t)(elem[r] >> 32) >> shift) & mask) : 0xffffffffu;
+    uint32_t digit = valid ? ((hash20((uint32_t)(elem[r] >> 32)) >> shift) & mask) : 0xffffffffu;
     uint32_t peers = __match_any_sync(0xffffffffu, digit);
     uint32_t leader = (uint32_t)__ffs((int)peers) - 1;
     uint32_t before = (uint32_t)__popc(peers & ((1u << lane) - 1));
@@ -205,7 +207,7 @@ k_sort_scatter(const uint64_t* in, uint64_t* out, const uint8_t* data, uint32_t 
     uint32_t i = base + r * 32 + lane;
     if (i < n)
     {
-      uint32_t digit = ((uint32_t)(elem[r] >> 32) >> shift) & mask;
+      uint32_t digit = (hash20((uint32_t)(elem[r] >> 32)) >> shift) & mask;
       out[cnt[warp][digit] + rank[r]] = elem[r];
     }
   }
