@@ -60,23 +60,48 @@ k_chain(const uint64_t* sorted, uint32_t n, uint16_t* pe, Geom g)
   const uint64_t e = sorted[r];
   const uint32_t p = (uint32_t)e, four = (uint32_t)(e >> 32), h = hash20(four);
   const uint32_t floor_pos = floor_of(g, p);
-  uint32_t result = 0, total = 0, at = p;
-  for (uint32_t k = r; k > 0; )
+  // The only chain member with a zeroed ring entry a walk from p can meet is the twice-inserted position of the
+  // nearest block border behind p (blocks are longer than the window).  A link across a legacy block needs no
+  // test of its own: its target lies below floor_pos, which ends the walk with the same "no match".
+  uint32_t zeroed = 0xffffffffu;
+  if (!g.legacy && p + kEndNoMatch >= g.halo)
   {
-    k--;
-    const uint64_t e0 = sorted[k];
+    const uint32_t x = g.halo + (p + kEndNoMatch - g.halo) / g.block_size * g.block_size;
+    if (x >= kEndNoMatch && x - kEndNoMatch < p && is_twice_inserted(g, x - kEndNoMatch)) zeroed = x - kEndNoMatch;
+  }
+  uint32_t result = 0, total = 0, at = p;
+  // one chain member: true when the walk is over
+  auto visit = [&](uint64_t e0) -> bool
+  {
     const uint32_t w = (uint32_t)(e0 >> 32), q = (uint32_t)e0;
-    if (hash20(w) != h) break;                                 // front of the hash class
-    // the link at -> q is `at`'s ring entry: zero for a position the next block has inserted again (its own walk,
-    // at == p, still saw the value: k_twice_save / own_entry)
-    const uint32_t step = (at != p && is_twice_inserted(g, at)) ? 0u : hash_link(g, at, q);
-    if (step == 0) break;
+    if (hash20(w) != h) return true;                           // front of the hash class
+    if (at == zeroed) return true;                             // ring entry zeroed by the next block's lookback (Q-twice)
+    const uint32_t step = at - q;
+    if (step > kWindow) return true;                           // smallz4.h:668
     total += step;
-    if (total > kWindow) break;
-    if (q < floor_pos) break;                                  // in front of the reference's buffer (UB-1): "no match"
-    if (w == four) { result = total; break; }
-    if (total == kWindow) break;
+    if (total > kWindow) return true;
+    if (q < floor_pos) return true;                            // in front of the reference's buffer (UB-1): "no match"
+    if (w == four) { result = total; return true; }
+    if (total == kWindow) return true;
     at = q;
+    return false;
+  };
+  // nearly every walk ends at its first or second member; the few that go on (another frequent word in the same
+  // hash class, e.g. a colliding word inside a long run) fetch eight members at a time so that the loads overlap
+  uint32_t k = r;
+  bool done = k == 0;
+  for (uint32_t i = 0; i < 2 && !done; i++) { k--; done = visit(sorted[k]) || k == 0; }
+  while (!done)
+  {
+    const uint32_t nb = min(k, 8u);
+    uint64_t eb[8];
+#pragma unroll
+    for (uint32_t i = 0; i < 8; i++) eb[i] = i < nb ? sorted[k - 1 - i] : 0;
+#pragma unroll
+    for (uint32_t i = 0; i < 8; i++)
+      if (!done && i < nb) done = visit(eb[i]);
+    k -= nb;
+    if (k == 0) done = true;
   }
   pe[p] = (uint16_t)result;
 }
