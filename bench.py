@@ -127,9 +127,11 @@ class ClockSampler(threading.Thread):
 
 # --------------------------------------------------------------------------- our arm (GPU)
 # algorithmic bytes per input position of each phase's dominant kernel (DESIGN.md "Kernels")
-PHASE_BYTES = {"sort": 3 * (8 + 8 + 8) + 1, "chain": 8 + 2 + 4 + 2 + 2, "search": 1 + 2 + 4 + 2, "fixup": 6,
+PHASE_BYTES = {"sort": 3 * (8 + 8 + 8) + 1, "chain": 8 + 2 + 1 + 4 + 2 + 2, "search": 1 + 2 + 4 + 2, "fixup": 6,
                "dp": 4 + 2 + 4 + 16, "path": 6, "emit": 2}
-PHASE_KERNEL = {"sort": "k_sort_scatter (+hist, scan)", "chain": "k_exact_walk (+k_link)", "search": "k_search",
+# DRAM bytes per input byte of the dominant kernels, from ncu --set full (profiles/r1_final_summary.md)
+DRAM_BYTES_PER_INPUT_BYTE = {"search": 16.1}
+PHASE_KERNEL = {"sort": "k_sort_scatter (+hist, scan)", "chain": "k_chain (+ run helpers k_flag_*)", "search": "k_search",
                 "fixup": "k_seed_detect/k_seed_fix", "dp": "k_dp", "path": "k_path", "emit": "k_emit"}
 
 
@@ -244,7 +246,8 @@ def run_ours(args, rank, world, local_rank):
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": workload_name(args.size_mb) + (f" per GPU, {world} shards with 128 KiB halos" if world > 1 else ""),
-                       "level": 9, "block_bytes": 4 * MB, "l2": "input (256 MB) larger than L2 (126 MB); no flush needed",
+                       "level": 9, "block_bytes": 4 * MB, "l2": (f"input ({args.size_mb} MB) larger than L2 (126 MB); no flush needed" if args.size_mb > 126
+                              else f"input ({args.size_mb} MB) fits L2: not a valid bench size"),
                        "batch_blocks": args.batch_blocks},
             "e2e": {"value": total * args.steps / dt_e2e / 1e9, "unit": "GB/s", "h2d_bytes_per_step": shard,
                     "d2h_bytes_per_step": int(frame_len) + 8 * ((shard // (args.batch_blocks * 4 * MB)) + 1)},
@@ -253,7 +256,11 @@ def run_ours(args, rank, world, local_rank):
             "phase_ms_per_step": {k: v / args.steps for k, v in phases.items()},
             "compression_ratio": shard / max(int(seg_len), 1),
             "roofline": {"bound": "hbm", "kernel": PHASE_KERNEL[top], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_kind,
+                         "frac": achieved / peak,
+                         "traffic": (int(DRAM_BYTES_PER_INPUT_BYTE[top] * shard) if top in DRAM_BYTES_PER_INPUT_BYTE else None),
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture at 64 MB "
+                                           "(profiles/r1_final_summary.md), scaled to this launch's input bytes",
+                         "peak_source": peak_kind,
                          "algorithmic_bytes_per_input_byte": PHASE_BYTES[top], "ms_per_launch": top_ms},
             "clocks": sampler.summary(),
         }

@@ -239,7 +239,10 @@ __device__ __forceinline__ bool walk_stretch(const SearchView& v, const uint32_t
 // lane states of the walk
 // kWalk: in the fast loop (the bytes a longer match needs first are staged); kSlowWalk: hops one candidate per round in the slow part
 enum : uint32_t { kIdle = 0, kWalk = 1, kCheck = 2, kStretch = 3, kFinish = 4, kSlowWalk = 5 };
-enum : uint32_t { kFastHops = 8 };
+#ifndef SZ4_FAST_BLOCK
+#define SZ4_FAST_BLOCK 8
+#endif
+enum : uint32_t { kFastHops = SZ4_FAST_BLOCK };   // candidates per lane between two looks at how many lanes still walk
 
 // The rejecting path of the walk (smallz4.h:192-233) for up to `hops` candidates per lane; see k_search.
 __device__ __forceinline__ void fast_hops_loop(const SearchView& v, uint32_t hops, uint32_t& state, uint32_t& total, uint32_t& hop,
