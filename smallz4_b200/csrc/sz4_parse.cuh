@@ -19,7 +19,7 @@
 //               registers and updates it whenever a cost above it is decided (4 instructions, all
 //               lanes at once); the decision for position l then only needs a shuffle from lane l
 //               and the scalar recurrence cost[l] = min(cost[l+1] + literal, best candidate).
-// The most recent kDpRing (1024) costs and table entries stay in shared-memory rings -- small enough for seven
+// The most recent kDpRing (512) costs and table entries stay in shared-memory rings -- small enough for eleven
 // single-warp CTAs per SM, which is what bounds the throughput of k_dp_spec; older ones come from L2/HBM.
 #pragma once
 #include "sz4_device.cuh"
@@ -45,7 +45,7 @@ __device__ __forceinline__ void take_better(uint32_t& best_cost, uint32_t& best_
 
 // Tunables of the segment-parallel DP (overridable for the emulated tests, which use small blocks)
 #ifndef SZ4_DP_RING
-#define SZ4_DP_RING 1024
+#define SZ4_DP_RING 512
 #endif
 #ifndef SZ4_DP_SEG
 #define SZ4_DP_SEG 32768
