@@ -57,7 +57,8 @@ k_chain(const uint64_t* sorted, uint32_t n, uint16_t* pe, Geom g)
 {
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
-  const uint64_t e = sorted[r];
+  // the element and its two predecessors are fetched together: nearly every walk ends at one of them
+  const uint64_t e = sorted[r], e1 = r >= 1 ? sorted[r - 1] : 0, e2 = r >= 2 ? sorted[r - 2] : 0;
   const uint32_t p = (uint32_t)e, four = (uint32_t)(e >> 32), h = hash20(four);
   const uint32_t floor_pos = floor_of(g, p);
   // The only chain member with a zeroed ring entry a walk from p can meet is the twice-inserted position of the
@@ -90,7 +91,8 @@ k_chain(const uint64_t* sorted, uint32_t n, uint16_t* pe, Geom g)
   // hash class, e.g. a colliding word inside a long run) fetch eight members at a time so that the loads overlap
   uint32_t k = r;
   bool done = k == 0;
-  for (uint32_t i = 0; i < 2 && !done; i++) { k--; done = visit(sorted[k]) || k == 0; }
+  if (!done) { k--; done = visit(e1) || k == 0; }
+  if (!done) { k--; done = visit(e2) || k == 0; }
   while (!done)
   {
     const uint32_t nb = min(k, 8u);
