@@ -43,6 +43,8 @@ struct sz4_ctx
   int          device = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t  ev0 = nullptr, ev1 = nullptr;
+  cudaStream_t copy_stream = nullptr;                 // input of the next batch / output of the previous one, next to the kernels
+  cudaEvent_t  ev_in = nullptr, ev_out[2] = { nullptr, nullptr };
   cudaEvent_t  pev[8] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
   double       phase_ms[7] = { 0, 0, 0, 0, 0, 0, 0 };   // sort, chain, search, fixup, dp, path, emit
   int          profile = 0;
@@ -57,6 +59,7 @@ struct sz4_ctx
   uint32_t dense_a = 256, dense_b = 2048;   // k_search: first-two-hops distance below which a position goes in the first / second pass (0 = one pass)
   uint32_t fast_lanes = 8;     // ... which goes on in steps of eight while at least this many lanes are still walking
   // device memory (grow-only)
+  DevBuf data2, seg2;                                  // the other halves of the double-buffered input and output
   DevBuf data, ph, pe, mlen, mdist, scratch, hist, hist_scanned, partials, seqs, seq_count, packed,
          saved_ph, saved_pe, seeds, nseeds, seg, block_out, seg_total, dbg_len, dbg_dist, scalar_state,
          run_fwd, ones_back, flag_last, flag_carry, mfin, dp_tasks, dp_count, dp_states, dp_overlays, dp_redo, dp_reach, seqs_tmp, path_segs;
@@ -437,13 +440,15 @@ static int compress_blocks(sz4_ctx* ctx, const StreamJob& job, size_t* out_len)
   if (scalar) per_batch = (uint32_t)blocks_total;                 // ring state lives in one launch
   if (scalar && job.n + kWindow > max_batch_bytes) { ctx->err = "dictionary stream with long runs is limited to 1 GiB"; return SZ4_ERR_ARG; }
 
-  size_t o = 0;
-  for (uint64_t kb = 0; kb < blocks_total; kb += per_batch)
+  // Batches are double-buffered: while the kernels of batch k run on ctx->stream, ctx->copy_stream brings in the
+  // input of batch k+1 and takes out the records of batch k-1.  run_batch always works on ctx->data / ctx->seg;
+  // the halves are swapped around it.  (run_batch returns after its kernels have finished: it reads the size.)
+  auto geometry = [&](uint64_t kb, Geom& g, size_t& pay_lo, size_t& pay_hi, bool& batch_first)
   {
     const uint64_t ke = kb + per_batch < blocks_total ? kb + per_batch : blocks_total;
-    const size_t pay_lo = (size_t)(kb * bs);
-    const size_t pay_hi = (size_t)(ke * bs) < job.n ? (size_t)(ke * bs) : job.n;
-    const bool batch_first = job.first && kb == 0;
+    pay_lo = (size_t)(kb * bs);
+    pay_hi = (size_t)(ke * bs) < job.n ? (size_t)(ke * bs) : job.n;
+    batch_first = job.first && kb == 0;
     size_t halo;
     if (batch_first) halo = with_dict ? kWindow : 0;
     else if (job.legacy) halo = 0;
@@ -452,7 +457,6 @@ static int compress_blocks(sz4_ctx* ctx, const StreamJob& job, size_t* out_len)
       size_t avail = pay_lo + job.halo_in_src;                     // history present in src
       halo = avail < kHaloBytes ? avail : kHaloBytes;
     }
-    Geom g;
     memset(&g, 0, sizeof(g));
     g.halo = (uint32_t)halo;
     g.n_total = (uint32_t)(halo + (pay_hi - pay_lo));
@@ -464,27 +468,58 @@ static int compress_blocks(sz4_ctx* ctx, const StreamJob& job, size_t* out_len)
     g.legacy = job.legacy ? 1 : 0;
     g.stream_first = batch_first ? 1 : 0;
     g.stream_last = (job.last && ke == blocks_total) ? 1 : 0;
-
-    RSV(data, (size_t)g.n_total + 2 * kPad + 64);
-    uint8_t* d = (uint8_t*)ctx->data.p;
-    CK(cudaMemsetAsync(d, 0, kPad, ctx->stream));
-    CK(cudaMemsetAsync(d + kPad + g.n_total, 0, kPad + 64, ctx->stream));
+  };
+  // input of the batch that starts at block kb -> ctx->data2, on the copy stream
+  auto fetch = [&](uint64_t kb) -> int
+  {
+    Geom g; size_t pay_lo, pay_hi; bool batch_first;
+    geometry(kb, g, pay_lo, pay_hi, batch_first);
+    RSV(data2, (size_t)g.n_total + 2 * kPad + 64);
+    uint8_t* d = (uint8_t*)ctx->data2.p;
+    CK(cudaMemsetAsync(d, 0, kPad, ctx->copy_stream));
+    CK(cudaMemsetAsync(d + kPad + g.n_total, 0, kPad + 64, ctx->copy_stream));
     if (batch_first && with_dict)
     {
-      CK(cudaMemcpyAsync(d + kPad, prefix.data(), kWindow, cudaMemcpyHostToDevice, ctx->stream));
-      CK(cudaMemcpyAsync(d + kPad + kWindow, job.src + job.halo_in_src + pay_lo, pay_hi - pay_lo, in_kind, ctx->stream));
+      CK(cudaMemcpyAsync(d + kPad, prefix.data(), kWindow, cudaMemcpyHostToDevice, ctx->copy_stream));
+      CK(cudaMemcpyAsync(d + kPad + kWindow, job.src + job.halo_in_src + pay_lo, pay_hi - pay_lo, in_kind, ctx->copy_stream));
     }
     else
-      CK(cudaMemcpyAsync(d + kPad, job.src + job.halo_in_src + pay_lo - halo, halo + (pay_hi - pay_lo), in_kind, ctx->stream));
+      CK(cudaMemcpyAsync(d + kPad, job.src + job.halo_in_src + pay_lo - g.halo, g.halo + (pay_hi - pay_lo), in_kind, ctx->copy_stream));
+    CK(cudaEventRecord(ctx->ev_in, ctx->copy_stream));
+    return SZ4_OK;
+  };
+
+  size_t o = 0;
+  int slot = 0;
+  bool out_pending[2] = { false, false };
+  { int r = fetch(0); if (r != SZ4_OK) return r; }
+  for (uint64_t kb = 0; kb < blocks_total; kb += per_batch)
+  {
+    Geom g; size_t pay_lo, pay_hi; bool batch_first;
+    geometry(kb, g, pay_lo, pay_hi, batch_first);
+    std::swap(ctx->data, ctx->data2);                              // ctx->data: this batch's input, on its way
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_in, 0));
+    if (kb + per_batch < blocks_total)
+    {
+      // ctx->data2 held the previous batch's input, whose kernels have finished
+      int r = fetch(kb + per_batch);
+      if (r != SZ4_OK) { cudaStreamSynchronize(ctx->copy_stream); return r; }
+    }
+    // ctx->seg is about to be written again: its last copy-out (two batches ago) must be over
+    if (out_pending[slot]) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_out[slot], 0));
 
     int r = run_batch(ctx, g, scalar);
-    if (r != SZ4_OK) return r;
+    if (r != SZ4_OK) { cudaStreamSynchronize(ctx->copy_stream); return r; }
     const size_t seg_len = (size_t)*ctx->h_seg_total;
-    if (o + seg_len > job.cap) { ctx->err = "destination too small"; return SZ4_ERR_DST_SMALL; }
-    CK(cudaMemcpyAsync(job.dst + o, ctx->seg.p, seg_len, out_kind, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    if (o + seg_len > job.cap) { cudaStreamSynchronize(ctx->copy_stream); ctx->err = "destination too small"; return SZ4_ERR_DST_SMALL; }
+    CK(cudaMemcpyAsync(job.dst + o, ctx->seg.p, seg_len, out_kind, ctx->copy_stream));
+    CK(cudaEventRecord(ctx->ev_out[slot], ctx->copy_stream));
+    out_pending[slot] = true;
+    std::swap(ctx->seg, ctx->seg2);
+    slot ^= 1;
     o += seg_len;
   }
+  CK(cudaStreamSynchronize(ctx->copy_stream));
   *out_len = o;
   return SZ4_OK;
 }
@@ -517,6 +552,10 @@ int sz4_create(sz4_ctx** out, int device)
       cudaEventCreate(&ctx->pev[2]) != cudaSuccess || cudaEventCreate(&ctx->pev[3]) != cudaSuccess ||
       cudaEventCreate(&ctx->pev[4]) != cudaSuccess || cudaEventCreate(&ctx->pev[5]) != cudaSuccess ||
       cudaEventCreate(&ctx->pev[6]) != cudaSuccess || cudaEventCreate(&ctx->pev[7]) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_in, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_out[0], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_out[1], cudaEventDisableTiming) != cudaSuccess ||
       cudaMallocHost((void**)&ctx->h_seg_total, 64) != cudaSuccess)
   {
     fprintf(stderr, "smallz4_b200: cannot initialise CUDA device %d\n", device);
@@ -533,7 +572,7 @@ void sz4_destroy(sz4_ctx* ctx)
 {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  DevBuf* all[] = { &ctx->data, &ctx->ph, &ctx->pe, &ctx->mlen, &ctx->mdist, &ctx->scratch, &ctx->hist, &ctx->hist_scanned,
+  DevBuf* all[] = { &ctx->data2, &ctx->seg2, &ctx->data, &ctx->ph, &ctx->pe, &ctx->mlen, &ctx->mdist, &ctx->scratch, &ctx->hist, &ctx->hist_scanned,
                     &ctx->partials, &ctx->seqs, &ctx->seq_count, &ctx->packed, &ctx->saved_ph, &ctx->saved_pe, &ctx->seeds,
                     &ctx->nseeds, &ctx->seg, &ctx->block_out, &ctx->seg_total, &ctx->dbg_len, &ctx->dbg_dist, &ctx->scalar_state,
                     &ctx->run_fwd, &ctx->ones_back, &ctx->flag_last, &ctx->flag_carry, &ctx->mfin, &ctx->dp_tasks,
@@ -544,6 +583,9 @@ void sz4_destroy(sz4_ctx* ctx)
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   for (int k = 0; k < 8; k++) if (ctx->pev[k]) cudaEventDestroy(ctx->pev[k]);
+  if (ctx->ev_in) cudaEventDestroy(ctx->ev_in);
+  for (int k = 0; k < 2; k++) if (ctx->ev_out[k]) cudaEventDestroy(ctx->ev_out[k]);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
