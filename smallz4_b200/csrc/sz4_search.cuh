@@ -427,6 +427,7 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
     // ---- slow part: candidates that passed the first byte, stretches, finished walks
     if (state >= kCheck)
     {
+      bool rejected = false;
       if (state == kSlowWalk)
       {
         // one hop of a lane whose match reaches beyond the staged bytes: every candidate gets the closer look,
@@ -438,6 +439,10 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
           total = tot2;
           hop = lds_u16(cbase - 2 * tot2);
           state = (run != 0 && hop == 1) ? kStretch : kCheck;
+          // p heads `run` equal bytes and already has a match at least that long: a candidate can only be longer
+          // if exactly as many of that byte follow it (fewer: its run ends first; more: p's does) -- one read
+          // instead of a comparison
+          rejected = state == kCheck && run != 0 && len >= run && run_fwd[p - total] != run;
         }
       }
       bool finish = state == kFinish;
@@ -446,7 +451,8 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
         const uint32_t len_in = len;
         // (a candidate that is worth a closer look and opens a stretch of its run goes to the closed form as well:
         // inside p's own run every candidate passes the filter)
-        if (state == kStretch || (run != 0 && hop == 1))
+        if (rejected) { }                                             // cannot be longer: on to the next candidate
+        else if (state == kStretch || (run != 0 && hop == 1))
         {
           finish = walk_stretch(v, run_fwd, ones_back, p, stop, run, total, hop, len, dist, budget, tail);
         }
@@ -455,6 +461,11 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
           dist = total;
           if (--budget == 0) finish = true;
         }
+        // p heads a run longer than the window and has a match as long as the run: no candidate can be longer (one
+        // in another run of that byte has fewer of them, or the two runs would be one; one in p's own run has more,
+        // so p's run ends first).  Without this, every position of a zero page behind binary data walks thousands
+        // of four-zero candidates through this slow part.
+        if (run > kWindow && len >= run) finish = true;
         if (len != len_in)
         {
           if (p + len + 1 > stop) finish = true;                     // smallz4.h:205: nothing longer fits
