@@ -59,6 +59,7 @@ struct sz4_ctx
   uint32_t dense_a = 256, dense_b = 2048;   // k_search: first-two-hops distance below which a position goes in the first / second pass (0 = one pass)
   uint32_t fast_lanes = 8;     // ... which goes on in steps of eight while at least this many lanes are still walking
   // device memory (grow-only)
+  DevBuf tile_order;                                   // k_search: run positions per tile, and the tiles in starting order
   DevBuf data2, seg2;                                  // the other halves of the double-buffered input and output
   DevBuf data, ph, pe, mlen, mdist, scratch, hist, hist_scanned, partials, seqs, seq_count, packed,
          saved_ph, saved_pe, seeds, nseeds, seg, block_out, seg_total, dbg_len, dbg_dist, scalar_state,
@@ -243,9 +244,15 @@ static int run_batch(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
         CK(cudaFuncSetAttribute(k_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSearchSmem));
         ctx->attr_set = true;
       }
-      LAUNCH(ctx, k_search, g.n_blocks * tiles_per_block, kSearchThreads, kSearchSmem, (const uint8_t*)data, (const uint16_t*)pe,
+      const uint32_t n_tiles = g.n_blocks * tiles_per_block;
+      RSV(tile_order, (size_t)n_tiles * 8 + 64);
+      uint32_t* tile_cost = (uint32_t*)ctx->tile_order.p;
+      uint32_t* tile_order = tile_cost + n_tiles;
+      LAUNCH(ctx, k_tile_cost, n_tiles, 256, 0, (const uint16_t*)pe, tiles_per_block, g, tile_cost);
+      LAUNCH(ctx, k_tile_order, 1, 256, 0, (const uint32_t*)tile_cost, n_tiles, tile_order);
+      LAUNCH(ctx, k_search, n_tiles, kSearchThreads, kSearchSmem, (const uint8_t*)data, (const uint16_t*)pe,
              (const uint32_t*)saved_pe, (const uint32_t*)ctx->run_fwd.p, (const uint16_t*)ctx->ones_back.p, mlen, mdist,
-             tiles_per_block, g, ctx->stage_bulk, ctx->fast_hops, ctx->fast_lanes, ctx->dense_a, ctx->dense_b);
+             tiles_per_block, g, ctx->stage_bulk, ctx->fast_hops, ctx->fast_lanes, ctx->dense_a, ctx->dense_b, (const uint32_t*)tile_order);
       PHASE(3);
       if (g.max_chain <= kLazyMax)
         LAUNCH(ctx, k_greedy_filter, div_up(g.n_blocks, 4), 128, 0, (const uint8_t*)data, (const uint16_t*)pe, (const uint32_t*)saved_pe, mlen, mdist, g);
@@ -572,7 +579,7 @@ void sz4_destroy(sz4_ctx* ctx)
 {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  DevBuf* all[] = { &ctx->data2, &ctx->seg2, &ctx->data, &ctx->ph, &ctx->pe, &ctx->mlen, &ctx->mdist, &ctx->scratch, &ctx->hist, &ctx->hist_scanned,
+  DevBuf* all[] = { &ctx->tile_order, &ctx->data2, &ctx->seg2, &ctx->data, &ctx->ph, &ctx->pe, &ctx->mlen, &ctx->mdist, &ctx->scratch, &ctx->hist, &ctx->hist_scanned,
                     &ctx->partials, &ctx->seqs, &ctx->seq_count, &ctx->packed, &ctx->saved_ph, &ctx->saved_pe, &ctx->seeds,
                     &ctx->nseeds, &ctx->seg, &ctx->block_out, &ctx->seg_total, &ctx->dbg_len, &ctx->dbg_dist, &ctx->scalar_state,
                     &ctx->run_fwd, &ctx->ones_back, &ctx->flag_last, &ctx->flag_carry, &ctx->mfin, &ctx->dp_tasks,

@@ -292,17 +292,69 @@ __device__ __forceinline__ void fast_hops_loop(const SearchView& v, uint32_t hop
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Order of the tiles.  A tile ends with its longest walk, and tiles full of byte runs (every other run of the
+// same byte in the window costs a round of the slow part) take up to 40 times the average: started last, one
+// of them keeps a single SM busy for milliseconds after all others are done.  So the tiles with many run
+// positions (previousExact == 1) are started first.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_tile_cost(const uint16_t* pe, uint32_t tiles_per_block, Geom g, uint32_t* cost)
+{
+  __shared__ uint32_t ws[32], tot;
+  const uint32_t j = blockIdx.x / tiles_per_block, t = blockIdx.x % tiles_per_block;
+  const uint32_t t0 = block_begin(g, j) + t * kTile, s_end = search_end(g, j);
+  uint32_t mine = 0;
+  if (t0 < s_end)
+  {
+    const uint32_t t1 = min(t0 + kTile, s_end);
+    for (uint32_t p = t0 + threadIdx.x; p < t1; p += blockDim.x) mine += pe[p] == 1 ? 1u : 0u;
+  }
+  (void)block_excl_scan(mine, ws, &tot);
+  if (threadIdx.x == 0) cost[blockIdx.x] = tot;
+}
+
+// one CTA: stable partition of the tile numbers into three classes (more than 3/4, more than 1/4 run positions, rest)
+__global__ void __launch_bounds__(256)
+k_tile_order(const uint32_t* cost, uint32_t n_tiles, uint32_t* order)
+{
+  __shared__ uint32_t ws[32], tot;
+  const uint32_t per = (n_tiles + blockDim.x - 1) / blockDim.x;
+  const uint32_t lo = min(threadIdx.x * per, n_tiles), hi = min(lo + per, n_tiles);
+  uint32_t base = 0;
+  for (uint32_t cls = 0; cls < 3; cls++)
+  {
+    uint32_t mine = 0;
+    for (uint32_t i = lo; i < hi; i++)
+    {
+      const uint32_t c = cost[i];
+      const uint32_t k = c > 3 * kTile / 4 ? 0u : (c > kTile / 4 ? 1u : 2u);
+      mine += k == cls ? 1u : 0u;
+    }
+    uint32_t at = base + block_excl_scan(mine, ws, &tot);
+    for (uint32_t i = lo; i < hi; i++)
+    {
+      const uint32_t c = cost[i];
+      const uint32_t k = c > 3 * kTile / 4 ? 0u : (c > kTile / 4 ? 1u : 2u);
+      if (k == cls) order[at++] = i;
+    }
+    base += tot;
+    __syncthreads();
+  }
+}
+
 __global__ void __launch_bounds__(kSearchThreads, 1)
 k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, const uint32_t* run_fwd,
          const uint16_t* ones_back, uint32_t* mlen, uint16_t* mdist, uint32_t tiles_per_block, Geom g, int use_bulk,
-         uint32_t fast_hops, uint32_t fast_lanes, uint32_t dense_a, uint32_t dense_b)
+         uint32_t fast_hops, uint32_t fast_lanes, uint32_t dense_a, uint32_t dense_b, const uint32_t* tile_order)
 {
   SZ4_DYN_SMEM(smem);
   __shared__ uint64_t bar;
   __shared__ uint32_t next_pos;
 
-  const uint32_t j = blockIdx.x / tiles_per_block;
-  const uint32_t t = blockIdx.x % tiles_per_block;
+  const uint32_t tile = tile_order != nullptr ? tile_order[blockIdx.x] : blockIdx.x;   // CTAs start in blockIdx order
+  const uint32_t j = tile / tiles_per_block;
+  const uint32_t t = tile % tiles_per_block;
   const uint32_t t0 = block_begin(g, j) + t * kTile;
   const uint32_t s_end = search_end(g, j);
   if (t0 >= s_end) return;
