@@ -792,13 +792,40 @@ __device__ __forceinline__ DpOverlay overlay_of(uint32_t* base, uint32_t task_in
   return o;
 }
 
+// Starting order of the tasks of k_dp_spec: the long ones first (a segment that could not be cut -- a run of
+// matches shorter than 65 299 each, the unforced tail of a long run -- takes several times the nominal segment,
+// and started last it would finish alone).  One CTA, stable partition into four classes by length.
+__global__ void __launch_bounds__(256)
+k_dp_task_order(const DpTask* tasks, const uint32_t* task_count, uint32_t max_seg, uint32_t n_tasks, uint32_t* order)
+{
+  __shared__ uint32_t ws[32], tot;
+  const uint32_t per = (n_tasks + blockDim.x - 1) / blockDim.x;
+  const uint32_t lo = min(threadIdx.x * per, n_tasks), hi = min(lo + per, n_tasks);
+  auto cls_of = [&](uint32_t i) -> uint32_t
+  {
+    if (i % max_seg >= task_count[i / max_seg]) return 3u;       // not a task
+    const uint32_t len = tasks[i].hi - tasks[i].lo;
+    return len >= 4 * kDpSeg ? 0u : (len >= 2 * kDpSeg ? 1u : 2u);
+  };
+  uint32_t base = 0;
+  for (uint32_t cls = 0; cls < 4; cls++)
+  {
+    uint32_t mine = 0;
+    for (uint32_t i = lo; i < hi; i++) mine += cls_of(i) == cls ? 1u : 0u;
+    uint32_t at = base + block_excl_scan(mine, ws, &tot);
+    for (uint32_t i = lo; i < hi; i++) if (cls_of(i) == cls) order[at++] = i;
+    base += tot;
+    __syncthreads();
+  }
+}
+
 __global__ void __launch_bounds__(32)
 k_dp_spec(const uint32_t* mlen, const uint16_t* mdist, uint32_t* mfin, DpScratch s, const DpTask* tasks,
-          const uint32_t* task_count, DpState* states, uint32_t* overlays, uint32_t max_seg, uint32_t* stats, Geom g)
+          const uint32_t* task_count, DpState* states, uint32_t* overlays, uint32_t max_seg, uint32_t* stats, const uint32_t* order, Geom g)
 {
   SZ4_DYN_SMEM(smem);
   const uint32_t warp = 0;
-  const uint32_t ti = blockIdx.x;                                // one task per (single-warp) CTA: tasks differ a lot in length
+  const uint32_t ti = order[blockIdx.x];                                // one task per (single-warp) CTA: tasks differ a lot in length
   const uint32_t j = ti / max_seg, k = ti % max_seg;
   if (j >= g.n_blocks || k >= task_count[j]) return;
   const DpTask t = tasks[ti];

@@ -59,6 +59,7 @@ struct sz4_ctx
   uint32_t dense_a = 256, dense_b = 2048;   // k_search: first-two-hops distance below which a position goes in the first / second pass (0 = one pass)
   uint32_t fast_lanes = 8;     // ... which goes on in steps of eight while at least this many lanes are still walking
   // device memory (grow-only)
+  DevBuf dp_order;                                     // k_dp_spec: its tasks in starting order
   DevBuf tile_order;                                   // k_search: run positions per tile, and the tiles in starting order
   DevBuf data2, seg2;                                  // the other halves of the double-buffered input and output
   DevBuf data, ph, pe, mlen, mdist, scratch, hist, hist_scanned, partials, seqs, seq_count, packed,
@@ -325,8 +326,11 @@ static int run_batch(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
     plan_in.chunk_reach = c_reach; plan_in.chunk_reach_nf = c_reach_nf; plan_in.chunk_first = c_first;
     LAUNCH(ctx, k_dp_plan, div_up(g.n_blocks, 4), 128, 0, plan_in, groups_per_block, (DpTask*)ctx->dp_tasks.p, (uint32_t*)ctx->dp_count.p,
            max_seg, g);
+    RSV(dp_order, (size_t)n_tasks * 4 + 64);
+    LAUNCH(ctx, k_dp_task_order, 1, 256, 0, (const DpTask*)ctx->dp_tasks.p, (const uint32_t*)ctx->dp_count.p, max_seg, n_tasks,
+           (uint32_t*)ctx->dp_order.p);
     LAUNCH(ctx, k_dp_spec, n_tasks, 32, kDpSmemSpec, (const uint32_t*)mlen, (const uint16_t*)mdist, mfin, dp, (const DpTask*)ctx->dp_tasks.p,
-           (const uint32_t*)ctx->dp_count.p, (DpState*)ctx->dp_states.p, (uint32_t*)ctx->dp_overlays.p, max_seg, (uint32_t*)ctx->dp_redo.p, g);
+           (const uint32_t*)ctx->dp_count.p, (DpState*)ctx->dp_states.p, (uint32_t*)ctx->dp_overlays.p, max_seg, (uint32_t*)ctx->dp_redo.p, (const uint32_t*)ctx->dp_order.p, g);
     LAUNCH(ctx, k_dp_verify, div_up(g.n_blocks, 4), 128, 4 * kDpSmem, (const uint32_t*)mlen, (const uint16_t*)mdist, mfin, dp, (const DpTask*)ctx->dp_tasks.p,
            (const uint32_t*)ctx->dp_count.p, (DpState*)ctx->dp_states.p, (uint32_t*)ctx->dp_overlays.p, max_seg,
            (uint32_t*)ctx->dp_redo.p, ctx->debug_keep == 0, (const uint32_t*)reach_before, groups_per_block, g);
@@ -579,7 +583,7 @@ void sz4_destroy(sz4_ctx* ctx)
 {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  DevBuf* all[] = { &ctx->tile_order, &ctx->data2, &ctx->seg2, &ctx->data, &ctx->ph, &ctx->pe, &ctx->mlen, &ctx->mdist, &ctx->scratch, &ctx->hist, &ctx->hist_scanned,
+  DevBuf* all[] = { &ctx->dp_order, &ctx->tile_order, &ctx->data2, &ctx->seg2, &ctx->data, &ctx->ph, &ctx->pe, &ctx->mlen, &ctx->mdist, &ctx->scratch, &ctx->hist, &ctx->hist_scanned,
                     &ctx->partials, &ctx->seqs, &ctx->seq_count, &ctx->packed, &ctx->saved_ph, &ctx->saved_pe, &ctx->seeds,
                     &ctx->nseeds, &ctx->seg, &ctx->block_out, &ctx->seg_total, &ctx->dbg_len, &ctx->dbg_dist, &ctx->scalar_state,
                     &ctx->run_fwd, &ctx->ones_back, &ctx->flag_last, &ctx->flag_carry, &ctx->mfin, &ctx->dp_tasks,
