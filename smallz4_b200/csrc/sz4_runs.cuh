@@ -54,21 +54,29 @@ __global__ void __launch_bounds__(32) k_flag_carry(const uint32_t* chunk_last, u
   if (blockIdx.x != 0) return;
   const uint32_t lane = threadIdx.x;
   uint32_t run = 0;                                    // index + 1 of the last flag so far, 0 = none
-  for (uint32_t c0 = 0; c0 < chunks; c0 += 32)
+  // four steps of 32 chunks per round, their loads issued together (the scan itself is a dependent chain)
+  for (uint32_t c0 = 0; c0 < chunks; c0 += 128)
   {
-    const uint32_t c = c0 + lane;
-    const uint32_t v = c < chunks ? chunk_last[c] : SZ4_NOFLAG;
-    uint32_t incl = v == SZ4_NOFLAG ? 0 : v + 1;       // flags only move right: a later one is larger
+    uint32_t vv[4];
 #pragma unroll
-    for (uint32_t d = 1; d < 32; d <<= 1)
+    for (uint32_t u = 0; u < 4; u++) { const uint32_t c = c0 + 32 * u + lane; vv[u] = c < chunks ? chunk_last[c] : SZ4_NOFLAG; }
+#pragma unroll
+    for (uint32_t u = 0; u < 4; u++)
     {
-      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-      if (lane >= d) incl = max(incl, t);
+      const uint32_t c = c0 + 32 * u + lane;
+      const uint32_t v = vv[u];
+      uint32_t incl = v == SZ4_NOFLAG ? 0 : v + 1;     // flags only move right: a later one is larger
+#pragma unroll
+      for (uint32_t d = 1; d < 32; d <<= 1)
+      {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl = max(incl, t);
+      }
+      uint32_t before = __shfl_up_sync(0xffffffffu, incl, 1);
+      before = lane == 0 ? run : max(before, run);
+      if (c < chunks) chunk_carry[c] = before ? before - 1 : SZ4_NOFLAG;
+      run = max(run, __shfl_sync(0xffffffffu, incl, 31));
     }
-    uint32_t before = __shfl_up_sync(0xffffffffu, incl, 1);
-    before = lane == 0 ? run : max(before, run);
-    if (c < chunks) chunk_carry[c] = before ? before - 1 : SZ4_NOFLAG;
-    run = max(run, __shfl_sync(0xffffffffu, incl, 31));
   }
 }
 
