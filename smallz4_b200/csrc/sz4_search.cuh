@@ -602,6 +602,8 @@ k_seed_fix(uint32_t* mlen, uint16_t* mdist, const Seed* seeds, const uint32_t* n
 // per block) replays the reference's skipMatches / lazyEvaluation state machine and the long-run
 // shortcut, and clears the matches the reference would not have looked for.
 // ---------------------------------------------------------------------------------------------
+enum : uint32_t { kGreedyChunk = 8 };   // windows of 32 positions fetched ahead together
+
 __global__ void __launch_bounds__(128)
 k_greedy_filter(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, uint32_t* mlen, uint16_t* mdist, Geom g)
 {
@@ -618,18 +620,47 @@ k_greedy_filter(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_p
   bool peek = false;            // lazyEvaluation
   uint32_t seed = 0xffffffffu;  // last position in front of a stretch the long-run shortcut skipped
   uint32_t at = b;              // next position to look at
-  // the reference walks position by position; here a window of 32 positions is loaded at once and the
-  // state machine advances from event to event (a searched position, or a batch of skipped ones)
+  // The reference walks position by position; here a window of 32 positions is looked at at once and the
+  // state machine advances from event to event (a searched position, or a batch of skipped ones).  The windows
+  // come in chunks of eight: while one chunk is worked on out of shared memory, the loads of the next one are in
+  // flight (a window takes far less time than a DRAM round trip; nothing the loop writes is read again, except
+  // behind a jump over a long run, where the chunks are fetched anew).
+  __shared__ uint32_t q_all[4][3][kGreedyChunk * 32];
+  uint32_t* q_own = q_all[threadIdx.x >> 5][0];
+  uint32_t* q_len = q_all[threadIdx.x >> 5][1];
+  uint32_t* q_dist = q_all[threadIdx.x >> 5][2];
+  uint32_t n_own[kGreedyChunk], n_len[kGreedyChunk], n_dist[kGreedyChunk];
+  auto fetch = [&](uint32_t cb)                                  // chunk that starts at position cb -> registers
+  {
+#pragma unroll
+    for (uint32_t k = 0; k < kGreedyChunk; k++)
+    {
+      const uint32_t q = cb + k * 32 + lane;
+      n_own[k] = 0; n_len[k] = 0; n_dist[k] = 0;
+      if (q < s_end) { n_own[k] = (tw && q == tw_pos) ? tw_own : pe[q]; n_len[k] = mlen[q]; n_dist[k] = mdist[q]; }
+    }
+  };
+  auto commit = [&]()
+  {
+#pragma unroll
+    for (uint32_t k = 0; k < kGreedyChunk; k++) { q_own[k * 32 + lane] = n_own[k]; q_len[k * 32 + lane] = n_len[k]; q_dist[k * 32 + lane] = n_dist[k]; }
+  };
+  uint32_t chunk = b;                                            // first position of the chunk in shared memory
+  fetch(chunk); commit(); fetch(chunk + kGreedyChunk * 32);
   while (at < s_end)
   {
     const uint32_t w = b + ((at - b) & ~31u);
     const uint32_t p = w + lane;
-    uint32_t own = 0, fl = 0, fd = 0;
-    if (p < s_end)
+    if (w - chunk >= kGreedyChunk * 32)
     {
-      own = (tw && p == tw_pos) ? tw_own : pe[p];
-      fl = mlen[p]; fd = mdist[p];
+      const uint32_t cb = b + (w - b) / (kGreedyChunk * 32) * (kGreedyChunk * 32);
+      if (cb != chunk + kGreedyChunk * 32) fetch(cb);            // a jump: what is in flight is not what comes next
+      chunk = cb;
+      commit();
+      fetch(chunk + kGreedyChunk * 32);
     }
+    const uint32_t qi = (w - chunk) + lane;
+    uint32_t own = q_own[qi], fl = q_len[qi], fd = q_dist[qi];
     if (seed != 0xffffffffu && p == at && g.shift == 0 && p < s_end)
     {
       // first position behind a skipped stretch: its predecessor in every chain is the seed
