@@ -59,6 +59,7 @@ struct sz4_ctx
   uint32_t dense_a = 256, dense_b = 2048;   // k_search: first-two-hops distance below which a position goes in the first / second pass (0 = one pass)
   uint32_t fast_lanes = 8;     // ... which goes on in steps of eight while at least this many lanes are still walking
   // device memory (grow-only)
+  DevBuf greedy_segs;                                  // k_greedy_*: entry / leave of every segment, and the number of second walks
   DevBuf dp_order;                                     // k_dp_spec: its tasks in starting order
   DevBuf tile_order;                                   // k_search: run positions per tile, and the tiles in starting order
   DevBuf data2, seg2;                                  // the other halves of the double-buffered input and output
@@ -256,7 +257,18 @@ static int run_batch(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
              tiles_per_block, g, ctx->stage_bulk, ctx->fast_hops, ctx->fast_lanes, ctx->dense_a, ctx->dense_b, (const uint32_t*)tile_order);
       PHASE(3);
       if (g.max_chain <= kLazyMax)
-        LAUNCH(ctx, k_greedy_filter, div_up(g.n_blocks, 4), 128, 0, (const uint8_t*)data, (const uint16_t*)pe, (const uint32_t*)saved_pe, mlen, mdist, g);
+      {
+        // greedy / lazy levels: which positions the reference would have searched at all (sz4_search.cuh, k_greedy_*)
+        const uint32_t segs_per_block = div_up(g.block_size, kGreedySeg);
+        const uint32_t n_segs = g.n_blocks * segs_per_block;
+        RSV(greedy_segs, (size_t)n_segs * sizeof(GreedySeg) + 128);
+        GreedySeg* gsegs = (GreedySeg*)ctx->greedy_segs.p;
+        uint32_t* gredo = (uint32_t*)(gsegs + n_segs);
+        CK(cudaMemsetAsync(gredo, 0, 4, ctx->stream));
+        LAUNCH(ctx, k_greedy_spec, div_up(n_segs, 4), 128, 0, (const uint16_t*)pe, (const uint32_t*)saved_pe, mlen, mdist, gsegs, segs_per_block, g);
+        LAUNCH(ctx, k_greedy_join, div_up(g.n_blocks, 4), 128, 0, (const uint16_t*)pe, (const uint32_t*)saved_pe, mlen, mdist, gsegs, segs_per_block, gredo, g);
+        LAUNCH(ctx, k_greedy_apply, div_up(n_segs, 4), 128, 0, (const uint16_t*)pe, (const uint32_t*)saved_pe, mlen, mdist, (const GreedySeg*)gsegs, segs_per_block, g);
+      }
       else
       {
         CK(cudaMemsetAsync(ctx->nseeds.p, 0, 4, ctx->stream));
@@ -583,7 +595,7 @@ void sz4_destroy(sz4_ctx* ctx)
 {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  DevBuf* all[] = { &ctx->dp_order, &ctx->tile_order, &ctx->data2, &ctx->seg2, &ctx->data, &ctx->ph, &ctx->pe, &ctx->mlen, &ctx->mdist, &ctx->scratch, &ctx->hist, &ctx->hist_scanned,
+  DevBuf* all[] = { &ctx->greedy_segs, &ctx->dp_order, &ctx->tile_order, &ctx->data2, &ctx->seg2, &ctx->data, &ctx->ph, &ctx->pe, &ctx->mlen, &ctx->mdist, &ctx->scratch, &ctx->hist, &ctx->hist_scanned,
                     &ctx->partials, &ctx->seqs, &ctx->seq_count, &ctx->packed, &ctx->saved_ph, &ctx->saved_pe, &ctx->seeds,
                     &ctx->nseeds, &ctx->seg, &ctx->block_out, &ctx->seg_total, &ctx->dbg_len, &ctx->dbg_dist, &ctx->scalar_state,
                     &ctx->run_fwd, &ctx->ones_back, &ctx->flag_last, &ctx->flag_carry, &ctx->mfin, &ctx->dp_tasks,

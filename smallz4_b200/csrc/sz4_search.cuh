@@ -598,57 +598,77 @@ k_seed_fix(uint32_t* mlen, uint16_t* mdist, const Seed* seeds, const uint32_t* n
 
 // ---------------------------------------------------------------------------------------------
 // Levels 1..6 (smallz4.h:606-612, 727-743): greedy / lazy levels search only some positions.
-// k_search has produced the match of every eligible position; this sequential pass (one thread
-// per block) replays the reference's skipMatches / lazyEvaluation state machine and the long-run
-// shortcut, and clears the matches the reference would not have looked for.
+// k_search has produced the match of every eligible position; the passes below replay the reference's
+// skipMatches / lazyEvaluation state machine and the long-run shortcut, and clear the matches the
+// reference would not have looked for -- in segments, see k_greedy_spec / k_greedy_join / k_greedy_apply.
 // ---------------------------------------------------------------------------------------------
-enum : uint32_t { kGreedyChunk = 8 };   // windows of 32 positions fetched ahead together
-
-__global__ void __launch_bounds__(128)
-k_greedy_filter(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, uint32_t* mlen, uint16_t* mdist, Geom g)
+#ifndef SZ4_GREEDY_SEG
+#define SZ4_GREEDY_SEG 32768
+#endif
+#ifndef SZ4_GREEDY_WARM
+#define SZ4_GREEDY_WARM 2048
+#endif
+enum : uint32_t
 {
-  (void)data;
-  const uint32_t j = blockIdx.x * 4 + (threadIdx.x >> 5);        // one block per warp, four warps per CTA
-  if (j >= g.n_blocks) return;
-  const uint32_t b = block_begin(g, j), s_end = search_end(g, j);
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t tw_pos = block_end(g, j) - kEndNoMatch;         // the only position whose own entry is in saved_pe
-  const bool tw = block_len(g, j) >= kEndNoMatch && is_twice_inserted(g, tw_pos);
-  const uint32_t tw_own = tw ? saved_pe[(tw_pos + kEndNoMatch - g.halo) / g.block_size] : 0;
+  kGreedyChunk = 8,                 // windows of 32 positions fetched ahead together
+  kGreedySeg   = SZ4_GREEDY_SEG,    // positions per segment (a multiple of 256)
+  kGreedyWarm  = SZ4_GREEDY_WARM    // positions a speculative walk starts in front of its segment
+};
 
+struct GreedyBlock                  // what the walk needs to know about its block
+{
+  uint32_t b, s_end, tw_pos, tw_own; bool tw;
+};
+__device__ __forceinline__ GreedyBlock greedy_block(const uint32_t* saved_pe, const Geom& g, uint32_t j)
+{
+  GreedyBlock k;
+  k.b = block_begin(g, j); k.s_end = search_end(g, j);
+  k.tw_pos = block_end(g, j) - kEndNoMatch;                      // the only position whose own entry is in saved_pe
+  k.tw = block_len(g, j) >= kEndNoMatch && is_twice_inserted(g, k.tw_pos);
+  k.tw_own = k.tw ? saved_pe[(k.tw_pos + kEndNoMatch - g.halo) / g.block_size] : 0;
+  return k;
+}
+
+// The reference's skipMatches / lazyEvaluation state machine (smallz4.h:727-743) and its long-run shortcut
+// (smallz4.h:632-643) from position `at` on, entered with nothing left to skip.  It runs until it is again in
+// that state at or behind `until` (or the block's positions are used up) and returns where.  kWrite = false
+// only follows the decisions; kWrite = true also clears the matches the reference would not have looked for.
+// The reference walks position by position; here a window of 32 positions is looked at at once and the
+// state machine advances from event to event (a searched position, or a batch of skipped ones).  The windows
+// come in chunks of eight: while one chunk is worked on out of shared memory, the loads of the next one are in
+// flight (a window takes far less time than a DRAM round trip; nothing the loop writes is read again, except
+// behind a jump over a long run, where the chunks are fetched anew).
+template <bool kWrite>
+__device__ __forceinline__ uint32_t greedy_walk(const GreedyBlock& k, const uint16_t* pe, uint32_t* mlen, uint16_t* mdist, const Geom& g,
+                                                uint32_t at, uint32_t until, uint32_t* q_own, uint32_t* q_len, uint32_t* q_dist)
+{
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t b = k.b, s_end = k.s_end;
   uint32_t skip = 0;            // skipMatches
   bool peek = false;            // lazyEvaluation
   uint32_t seed = 0xffffffffu;  // last position in front of a stretch the long-run shortcut skipped
-  uint32_t at = b;              // next position to look at
-  // The reference walks position by position; here a window of 32 positions is looked at at once and the
-  // state machine advances from event to event (a searched position, or a batch of skipped ones).  The windows
-  // come in chunks of eight: while one chunk is worked on out of shared memory, the loads of the next one are in
-  // flight (a window takes far less time than a DRAM round trip; nothing the loop writes is read again, except
-  // behind a jump over a long run, where the chunks are fetched anew).
-  __shared__ uint32_t q_all[4][3][kGreedyChunk * 32];
-  uint32_t* q_own = q_all[threadIdx.x >> 5][0];
-  uint32_t* q_len = q_all[threadIdx.x >> 5][1];
-  uint32_t* q_dist = q_all[threadIdx.x >> 5][2];
   uint32_t n_own[kGreedyChunk], n_len[kGreedyChunk], n_dist[kGreedyChunk];
   auto fetch = [&](uint32_t cb)                                  // chunk that starts at position cb -> registers
   {
 #pragma unroll
-    for (uint32_t k = 0; k < kGreedyChunk; k++)
+    for (uint32_t i = 0; i < kGreedyChunk; i++)
     {
-      const uint32_t q = cb + k * 32 + lane;
-      n_own[k] = 0; n_len[k] = 0; n_dist[k] = 0;
-      if (q < s_end) { n_own[k] = (tw && q == tw_pos) ? tw_own : pe[q]; n_len[k] = mlen[q]; n_dist[k] = mdist[q]; }
+      const uint32_t q = cb + i * 32 + lane;
+      n_own[i] = 0; n_len[i] = 0; n_dist[i] = 0;
+      if (q < s_end) { n_own[i] = (k.tw && q == k.tw_pos) ? k.tw_own : pe[q]; n_len[i] = mlen[q]; n_dist[i] = mdist[q]; }
     }
   };
   auto commit = [&]()
   {
 #pragma unroll
-    for (uint32_t k = 0; k < kGreedyChunk; k++) { q_own[k * 32 + lane] = n_own[k]; q_len[k * 32 + lane] = n_len[k]; q_dist[k * 32 + lane] = n_dist[k]; }
+    for (uint32_t i = 0; i < kGreedyChunk; i++) { q_own[i * 32 + lane] = n_own[i]; q_len[i * 32 + lane] = n_len[i]; q_dist[i * 32 + lane] = n_dist[i]; }
   };
-  uint32_t chunk = b;                                            // first position of the chunk in shared memory
+  if (at >= s_end) return s_end;
+  uint32_t chunk = b + (at - b) / (kGreedyChunk * 32) * (kGreedyChunk * 32);   // first position of the chunk in shared memory
   fetch(chunk); commit(); fetch(chunk + kGreedyChunk * 32);
   while (at < s_end)
   {
+    if (skip == 0 && at >= until) return at;
     const uint32_t w = b + ((at - b) & ~31u);
     const uint32_t p = w + lane;
     if (w - chunk >= kGreedyChunk * 32)
@@ -665,8 +685,8 @@ k_greedy_filter(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_p
     {
       // first position behind a skipped stretch: its predecessor in every chain is the seed
       const uint32_t gap = p - seed;
-      if (gap > kWindow) { own = 0; mlen[p] = 0; mdist[p] = 0; }
-      else if (fd == 1) { fd = gap; mdist[p] = (uint16_t)gap; }
+      if (gap > kWindow) { own = 0; if (kWrite) { mlen[p] = 0; mdist[p] = 0; } }
+      else if (fd == 1) { fd = gap; if (kWrite) mdist[p] = (uint16_t)gap; }
     }
     seed = 0xffffffffu;
     const uint32_t eligible = __ballot_sync(0xffffffffu, own != 0);
@@ -674,6 +694,7 @@ k_greedy_filter(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_p
     bool jumped = false;
     while (o < 32)
     {
+      if (skip == 0 && w + o >= until) return w + o;
       const uint32_t rem = eligible & (0xffffffffu << o);
       if (rem == 0) break;
       if (skip > 0 && !peek)
@@ -682,11 +703,11 @@ k_greedy_filter(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_p
         const uint32_t c = (uint32_t)__popc(rem), t = min(c, skip);
         const uint32_t rank = (uint32_t)__popc(rem & ((2u << lane) - 1));      // 1-based among the remaining eligible lanes
         const bool mine = ((rem >> lane) & 1u) && rank <= t;
-        if (mine) { mlen[p] = 0; mdist[p] = 0; }
+        if (kWrite && mine) { mlen[p] = 0; mdist[p] = 0; }
         skip -= t;
-        if (t == c) break;
         const uint32_t last = __ballot_sync(0xffffffffu, mine && rank == t);
         o = (uint32_t)__ffs((int)last);                                        // lane of the t-th one, plus one
+        if (t == c) { if (skip != 0) break; continue; }                        // (nothing left to skip: may be where to stop)
         continue;
       }
       // a searched position: the first remaining eligible one
@@ -700,7 +721,7 @@ k_greedy_filter(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_p
       {
         // smallz4.h:632-643: the following positions copy {length-1, 1} and are not inserted
         const uint32_t s = w + (uint32_t)l, count = L - kSameLetter;
-        for (uint32_t k = 1 + lane; k <= count; k += 32) { mlen[s + k] = L - k; mdist[s + k] = 1; }
+        if (kWrite) for (uint32_t i = 1 + lane; i <= count; i += 32) { mlen[s + i] = L - i; mdist[s + i] = 1; }
         seed = s;
         at = s + count + 1;
         jumped = true;
@@ -710,6 +731,82 @@ k_greedy_filter(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_p
     if (!jumped) at = w + 32;
     __syncwarp();
   }
+  return s_end;
+}
+
+// Levels 1..6 in three steps.  The state of the machine is "eligible positions still to skip", and it is zero again
+// behind every skipped stretch; two walks that are in that state in front of the same position stay together.  So:
+// k_greedy_spec: every segment of kGreedySeg positions is walked (decisions only) from kGreedyWarm positions in front
+//                of it; `entry` = where the walk first has nothing to skip inside the segment, `leave` = the same for
+//                the next segment.
+// k_greedy_join: one warp per block checks entry[k] == leave[k-1] from the first segment on (the first one starts in
+//                the true state) and walks again, from the true entry, wherever that fails.
+// k_greedy_apply: every segment is walked once more from its true entry, this time clearing the matches.
+struct GreedySeg { uint32_t entry, leave; };
+
+__global__ void __launch_bounds__(128)
+k_greedy_spec(const uint16_t* pe, const uint32_t* saved_pe, uint32_t* mlen, uint16_t* mdist, GreedySeg* segs, uint32_t segs_per_block, Geom g)
+{
+  __shared__ uint32_t q_all[4][3][kGreedyChunk * 32];
+  const uint32_t wi = threadIdx.x >> 5;
+  const uint32_t id = blockIdx.x * 4 + wi;
+  const uint32_t j = id / segs_per_block, sk = id % segs_per_block;
+  if (j >= g.n_blocks) return;
+  const GreedyBlock k = greedy_block(saved_pe, g, j);
+  const uint32_t s0 = k.b + sk * kGreedySeg;
+  GreedySeg r; r.entry = k.s_end; r.leave = k.s_end;
+  if (s0 < k.s_end)
+  {
+    const uint32_t from = sk == 0 ? k.b : s0 - kGreedyWarm;      // (segments are longer than the warm-up)
+    r.entry = sk == 0 ? k.b : greedy_walk<false>(k, pe, mlen, mdist, g, from, s0, q_all[wi][0], q_all[wi][1], q_all[wi][2]);
+    r.leave = greedy_walk<false>(k, pe, mlen, mdist, g, r.entry, s0 + kGreedySeg, q_all[wi][0], q_all[wi][1], q_all[wi][2]);
+  }
+  if ((threadIdx.x & 31) == 0) segs[id] = r;
+}
+
+__global__ void __launch_bounds__(128)
+k_greedy_join(const uint16_t* pe, const uint32_t* saved_pe, uint32_t* mlen, uint16_t* mdist, GreedySeg* segs, uint32_t segs_per_block,
+              uint32_t* redo_count, Geom g)
+{
+  __shared__ uint32_t q_all[4][3][kGreedyChunk * 32];
+  const uint32_t wi = threadIdx.x >> 5;
+  const uint32_t j = blockIdx.x * 4 + wi;
+  if (j >= g.n_blocks) return;
+  const GreedyBlock k = greedy_block(saved_pe, g, j);
+  uint32_t at = k.b;                                             // true entry of the segment at hand
+  for (uint32_t sk = 0; sk < segs_per_block; sk++)
+  {
+    const uint32_t id = j * segs_per_block + sk;
+    const uint32_t s0 = k.b + sk * kGreedySeg;
+    if (s0 >= k.s_end) break;
+    GreedySeg r = segs[id];
+    uint32_t leave;
+    if (at >= s0 + kGreedySeg) leave = at;                       // the previous walk went right across this segment
+    else if (at == r.entry) leave = r.leave;
+    else
+    {
+      leave = greedy_walk<false>(k, pe, mlen, mdist, g, at, s0 + kGreedySeg, q_all[wi][0], q_all[wi][1], q_all[wi][2]);
+      if ((threadIdx.x & 31) == 0) atomicAdd(redo_count, 1u);
+    }
+    if ((threadIdx.x & 31) == 0) { r.entry = at; r.leave = leave; segs[id] = r; }
+    at = leave;
+  }
+}
+
+__global__ void __launch_bounds__(128)
+k_greedy_apply(const uint16_t* pe, const uint32_t* saved_pe, uint32_t* mlen, uint16_t* mdist, const GreedySeg* segs, uint32_t segs_per_block, Geom g)
+{
+  __shared__ uint32_t q_all[4][3][kGreedyChunk * 32];
+  const uint32_t wi = threadIdx.x >> 5;
+  const uint32_t id = blockIdx.x * 4 + wi;
+  const uint32_t j = id / segs_per_block, sk = id % segs_per_block;
+  if (j >= g.n_blocks) return;
+  const GreedyBlock k = greedy_block(saved_pe, g, j);
+  const uint32_t s0 = k.b + sk * kGreedySeg;
+  if (s0 >= k.s_end) return;
+  const GreedySeg r = segs[id];
+  if (r.entry >= s0 + kGreedySeg || r.entry >= k.s_end) return;  // nothing of this segment is looked at
+  (void)greedy_walk<true>(k, pe, mlen, mdist, g, r.entry, s0 + kGreedySeg, q_all[wi][0], q_all[wi][1], q_all[wi][2]);
 }
 
 }  // namespace sz4

@@ -18,7 +18,7 @@ def chk(tag,data,lvl):
 rnd=lambda n,s: corpus.make('random',n,s).tobytes()
 txt=lambda n,s: corpus.make('text',n,s).tobytes()
 binr=lambda n,s: corpus.make('binary',n,s).tobytes()
-for lvl in [9,5]:
+for lvl in [9,5,1,3]:
     chk('zeros+random', bytes(50000)+rnd(30000,1)+bytes(40000)+rnd(9000,2)+txt(30000,3), lvl)
     chk('text+random', txt(40000,1)+rnd(20000,1)+txt(40000,2)+rnd(20000,3)+txt(30000,4), lvl)
     chk('binary+random', binr(40000,1)+rnd(20000,1)+binr(40000,2)+rnd(5000,3)+binr(30000,4), lvl)
