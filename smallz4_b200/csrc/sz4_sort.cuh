@@ -189,9 +189,15 @@ k_sort_scatter(const uint64_t* in, uint64_t* out, const uint8_t* data, uint32_t 
     __syncwarp();
   }
   __syncthreads();
+  // Per digit: where its elements start inside the tile (lstart) and in the output (gbase), and where each warp's
+  // share starts inside the digit.  The tile is first put in digit order in shared memory and then written out
+  // with consecutive threads on consecutive addresses: a warp's store covers a few long runs instead of 32
+  // scattered 8-byte pieces.
+  __shared__ uint32_t lstart[kSortBins], gbase[kSortBins];
+  __shared__ uint64_t stage[kSortTile];
   if (threadIdx.x < kSortBins)
   {
-    uint32_t run = hist_scanned[threadIdx.x * num_tiles + blockIdx.x];
+    uint32_t run = 0;
 #pragma unroll
     for (uint32_t w = 0; w < kSortThreads / 32; w++)
     {
@@ -199,6 +205,26 @@ k_sort_scatter(const uint64_t* in, uint64_t* out, const uint8_t* data, uint32_t 
       cnt[w][threadIdx.x] = run;
       run += c;
     }
+    lstart[threadIdx.x] = run;                                  // for now: the number of elements of this digit in the tile
+    gbase[threadIdx.x] = hist_scanned[threadIdx.x * num_tiles + blockIdx.x];
+  }
+  __syncthreads();
+  if (warp == 0)
+  {
+    // exclusive scan of the 128 counts: four per lane
+    uint32_t c[kSortBins / 32], sum = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < kSortBins / 32; k++) { c[k] = lstart[lane * (kSortBins / 32) + k]; sum += c[k]; }
+    uint32_t incl = sum;
+#pragma unroll
+    for (uint32_t d = 1; d < 32; d <<= 1)
+    {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    uint32_t run = incl - sum;
+#pragma unroll
+    for (uint32_t k = 0; k < kSortBins / 32; k++) { lstart[lane * (kSortBins / 32) + k] = run; run += c[k]; }
   }
   __syncthreads();
 #pragma unroll
@@ -208,8 +234,17 @@ k_sort_scatter(const uint64_t* in, uint64_t* out, const uint8_t* data, uint32_t 
     if (i < n)
     {
       uint32_t digit = (hash20((uint32_t)(elem[r] >> 32)) >> shift) & mask;
-      out[cnt[warp][digit] + rank[r]] = elem[r];
+      stage[lstart[digit] + cnt[warp][digit] + rank[r]] = elem[r];
     }
+  }
+  __syncthreads();
+  const uint32_t tile_base = blockIdx.x * kSortTile;
+  const uint32_t tile_n = min((uint32_t)kSortTile, n - tile_base);
+  for (uint32_t k = threadIdx.x; k < tile_n; k += kSortThreads)
+  {
+    const uint64_t e = stage[k];
+    const uint32_t digit = (hash20((uint32_t)(e >> 32)) >> shift) & mask;
+    out[gbase[digit] + (k - lstart[digit])] = e;
   }
 }
 
