@@ -56,9 +56,9 @@ __global__ void __launch_bounds__(256)
 k_chain(const uint64_t* sorted, uint32_t n, uint16_t* pe, Geom g)
 {
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= n) return;
+  const bool valid = r < n;                                    // (no early exit: the warp works together further down)
   // the element and its two predecessors are fetched together: nearly every walk ends at one of them
-  const uint64_t e = sorted[r], e1 = r >= 1 ? sorted[r - 1] : 0, e2 = r >= 2 ? sorted[r - 2] : 0;
+  const uint64_t e = valid ? sorted[r] : 0, e1 = valid && r >= 1 ? sorted[r - 1] : 0, e2 = valid && r >= 2 ? sorted[r - 2] : 0;
   const uint32_t p = (uint32_t)e, four = (uint32_t)(e >> 32), h = hash20(four);
   const uint32_t floor_pos = floor_of(g, p);
   // The only chain member with a zeroed ring entry a walk from p can meet is the twice-inserted position of the
@@ -87,25 +87,50 @@ k_chain(const uint64_t* sorted, uint32_t n, uint16_t* pe, Geom g)
     at = q;
     return false;
   };
-  // nearly every walk ends at its first or second member; the few that go on (another frequent word in the same
-  // hash class, e.g. a colliding word inside a long run) fetch eight members at a time so that the loads overlap
+  // Nearly every walk ends at its first or second member.  The few that go on (another frequent word in the same hash
+  // class, e.g. a colliding word behind a long run: up to 65535 members) are taken over by the whole warp, 32 members
+  // per step: nothing in a step depends on the step before it (the sum of the links so far is p - q).
   uint32_t k = r;
-  bool done = k == 0;
+  bool done = !valid || k == 0;
   if (!done) { k--; done = visit(e1) || k == 0; }
   if (!done) { k--; done = visit(e2) || k == 0; }
-  while (!done)
+  const uint32_t lane = threadIdx.x & 31;
+  uint32_t pending = __ballot_sync(0xffffffffu, !done);
+  while (pending)
   {
-    const uint32_t nb = min(k, 8u);
-    uint64_t eb[8];
-#pragma unroll
-    for (uint32_t i = 0; i < 8; i++) eb[i] = i < nb ? sorted[k - 1 - i] : 0;
-#pragma unroll
-    for (uint32_t i = 0; i < 8; i++)
-      if (!done && i < nb) done = visit(eb[i]);
-    k -= nb;
-    if (k == 0) done = true;
+    const int src = __ffs((int)pending) - 1;
+    pending &= pending - 1;
+    uint32_t bk = __shfl_sync(0xffffffffu, k, src), bat = __shfl_sync(0xffffffffu, at, src);
+    const uint32_t bp = __shfl_sync(0xffffffffu, p, src), bfour = __shfl_sync(0xffffffffu, four, src);
+    const uint32_t bfloor = __shfl_sync(0xffffffffu, floor_pos, src), bzero = __shfl_sync(0xffffffffu, zeroed, src);
+    const uint32_t bh = hash20(bfour);
+    uint32_t found = 0;
+    for (;;)
+    {
+      const bool have = bk > lane;                             // member bk - 1 - lane of the sorted array
+      const uint64_t e0 = have ? sorted[bk - 1 - lane] : 0;
+      const uint32_t w = (uint32_t)(e0 >> 32), q = (uint32_t)e0;
+      uint32_t prev = __shfl_up_sync(0xffffffffu, q, 1);       // the member in front of it on the chain
+      if (lane == 0) prev = bat;
+      const uint32_t total_here = bp - q;
+      // the same tests in the same order as `visit`
+      const bool dead = !have || hash20(w) != bh || prev == bzero || prev - q > kWindow || total_here > kWindow || q < bfloor;
+      const bool hit = !dead && w == bfour;
+      const bool stop = dead || hit || total_here == kWindow;
+      const uint32_t stops = __ballot_sync(0xffffffffu, stop);
+      if (stops != 0)
+      {
+        const int first = __ffs((int)stops) - 1;
+        found = __shfl_sync(0xffffffffu, hit ? total_here : 0u, first);
+        break;
+      }
+      bat = __shfl_sync(0xffffffffu, q, 31);
+      bk -= 32;
+      if (bk == 0) break;
+    }
+    if (lane == (uint32_t)src) result = found;
   }
-  pe[p] = (uint16_t)result;
+  if (valid) pe[p] = (uint16_t)result;
 }
 
 // one thread per block border k: position halo + k*block_size - 12
