@@ -45,8 +45,6 @@ struct sz4_ctx
   cudaEvent_t  ev0 = nullptr, ev1 = nullptr;
   cudaStream_t copy_stream = nullptr;                 // input of the next batch / output of the previous one, next to the kernels
   cudaEvent_t  ev_in = nullptr, ev_out[2] = { nullptr, nullptr };
-  cudaStream_t side_stream = nullptr;                 // run lengths of the input, next to the sort (they only need the bytes)
-  cudaEvent_t  ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t  pev[8] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
   double       phase_ms[7] = { 0, 0, 0, 0, 0, 0, 0 };   // sort, chain, search, fixup, dp, path, emit
   int          profile = 0;
@@ -93,11 +91,6 @@ struct sz4_ctx
 #define LAUNCH(ctx, kernel, grid, block, smem, ...)                        \
   do {                                                                     \
     SZ4_LAUNCH(kernel, grid, block, smem, (ctx)->stream, __VA_ARGS__);     \
-    (ctx)->launches++;                                                     \
-  } while (0)
-#define LAUNCH_SIDE(ctx, kernel, grid, block, smem, ...)                   \
-  do {                                                                     \
-    SZ4_LAUNCH(kernel, grid, block, smem, (ctx)->side_stream, __VA_ARGS__);\
     (ctx)->launches++;                                                     \
   } while (0)
 
@@ -188,24 +181,6 @@ static int run_batch(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
     const uint32_t count = N >= first + 4 ? N - 3 - first : 0;
     if (count > 0)
     {
-      // run_fwd only needs the bytes: its three kernels run on a side stream next to the sort
-      RSV(run_fwd, ((size_t)N + 64) * 4);
-      RSV(ones_back, ((size_t)N + 64) * 2);
-      if (g.shift == 0)
-      {
-        const uint32_t fchunks = div_up(N, kFlagChunk);
-        RSV(flag_last, (size_t)fchunks * 4 + 64);
-        RSV(flag_carry, (size_t)fchunks * 4 + 64);
-        uint32_t* fl = (uint32_t*)ctx->flag_last.p;
-        uint32_t* fc = (uint32_t*)ctx->flag_carry.p;
-        CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
-        CK(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
-        FlagFwdRuns fr; fr.data = data; fr.n = N;
-        LAUNCH_SIDE(ctx, k_flag_reduce<FlagFwdRuns>, fchunks, kFlagThreads, 0, fr, fl);
-        LAUNCH_SIDE(ctx, k_flag_carry, 1, 32, 0, (const uint32_t*)fl, fc, fchunks);
-        LAUNCH_SIDE(ctx, (k_flag_apply<FlagFwdRuns, uint32_t, true>), fchunks, kFlagThreads, 0, fr, (const uint32_t*)fc, (uint32_t*)ctx->run_fwd.p, 0xffffffffu);
-        CK(cudaEventRecord(ctx->ev_join, ctx->side_stream));
-      }
       uint64_t* bufA = (uint64_t*)ctx->scratch.p;
       uint64_t* bufB = bufA + (((size_t)N + kPad + 1) & ~(size_t)1);
       const uint32_t tiles = div_up(count, kSortTile);
@@ -246,13 +221,19 @@ static int run_batch(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
 
       PHASE(2);
       // ---- helpers for runs of one byte (sz4_runs.cuh): only the undisturbed ring (no dictionary) uses them
-      // (run_fwd was computed next to the sort, see above)
+      RSV(run_fwd, ((size_t)N + 64) * 4);
+      RSV(ones_back, ((size_t)N + 64) * 2);
       if (g.shift == 0)
       {
         const uint32_t fchunks = div_up(N, kFlagChunk);
+        RSV(flag_last, (size_t)fchunks * 4 + 64);
+        RSV(flag_carry, (size_t)fchunks * 4 + 64);
         uint32_t* fl = (uint32_t*)ctx->flag_last.p;
         uint32_t* fc = (uint32_t*)ctx->flag_carry.p;
-        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+        FlagFwdRuns fr; fr.data = data; fr.n = N;
+        LAUNCH(ctx, k_flag_reduce<FlagFwdRuns>, fchunks, kFlagThreads, 0, fr, fl);
+        LAUNCH(ctx, k_flag_carry, 1, 32, 0, (const uint32_t*)fl, fc, fchunks);
+        LAUNCH(ctx, (k_flag_apply<FlagFwdRuns, uint32_t, true>), fchunks, kFlagThreads, 0, fr, (const uint32_t*)fc, (uint32_t*)ctx->run_fwd.p, 0xffffffffu);
         FlagOnesBack fo; fo.pe = pe; fo.n = N;
         LAUNCH(ctx, k_flag_reduce<FlagOnesBack>, fchunks, kFlagThreads, 0, fo, fl);
         LAUNCH(ctx, k_flag_carry, 1, 32, 0, (const uint32_t*)fl, fc, fchunks);
@@ -595,9 +576,6 @@ int sz4_create(sz4_ctx** out, int device)
       cudaEventCreate(&ctx->pev[4]) != cudaSuccess || cudaEventCreate(&ctx->pev[5]) != cudaSuccess ||
       cudaEventCreate(&ctx->pev[6]) != cudaSuccess || cudaEventCreate(&ctx->pev[7]) != cudaSuccess ||
       cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->ev_in, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->ev_out[0], cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->ev_out[1], cudaEventDisableTiming) != cudaSuccess ||
@@ -628,9 +606,6 @@ void sz4_destroy(sz4_ctx* ctx)
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   for (int k = 0; k < 8; k++) if (ctx->pev[k]) cudaEventDestroy(ctx->pev[k]);
-  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
-  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
-  if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
   if (ctx->ev_in) cudaEventDestroy(ctx->ev_in);
   for (int k = 0; k < 2; k++) if (ctx->ev_out[k]) cudaEventDestroy(ctx->ev_out[k]);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
