@@ -295,8 +295,8 @@ __device__ __forceinline__ void fast_hops_loop(const SearchView& v, uint32_t hop
 // ---------------------------------------------------------------------------------------------
 // Order of the tiles.  A tile ends with its longest walk, and tiles full of byte runs (every other run of the
 // same byte in the window costs a round of the slow part) take up to 40 times the average: started last, one
-// of them keeps a single SM busy for milliseconds after all others are done.  So the tiles with many run
-// positions (previousExact == 1) are started first.
+// of them keeps a single SM busy for milliseconds after all others are done.  So the tiles are started in the
+// order of an estimate of that cost: run positions (previousExact == 1) times run heads.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_tile_cost(const uint16_t* pe, uint32_t tiles_per_block, Geom g, uint32_t* cost)
@@ -304,17 +304,36 @@ k_tile_cost(const uint16_t* pe, uint32_t tiles_per_block, Geom g, uint32_t* cost
   __shared__ uint32_t ws[32], tot;
   const uint32_t j = blockIdx.x / tiles_per_block, t = blockIdx.x % tiles_per_block;
   const uint32_t t0 = block_begin(g, j) + t * kTile, s_end = search_end(g, j);
-  uint32_t mine = 0;
+  // run positions (previousExact == 1) and run heads (the first of a stretch of them): a position inside a run
+  // pays one round of the slow part for every other run of its byte in the window
+  uint32_t mine = 0, heads = 0;
   if (t0 < s_end)
   {
     const uint32_t t1 = min(t0 + kTile, s_end);
-    for (uint32_t p = t0 + threadIdx.x; p < t1; p += blockDim.x) mine += pe[p] == 1 ? 1u : 0u;
+    for (uint32_t p = t0 + threadIdx.x; p < t1; p += blockDim.x)
+    {
+      const bool one = pe[p] == 1;
+      mine += one ? 1u : 0u;
+      heads += (one && pe[p - 1] != 1) ? 1u : 0u;              // (p >= 1: the arrays are padded in front)
+    }
   }
   (void)block_excl_scan(mine, ws, &tot);
-  if (threadIdx.x == 0) cost[blockIdx.x] = tot;
+  const uint32_t run_positions = tot;
+  __syncthreads();
+  (void)block_excl_scan(heads, ws, &tot);
+  if (threadIdx.x == 0)
+  {
+    const unsigned long long c = (unsigned long long)run_positions * (tot + 1);
+    cost[blockIdx.x] = c > 0xffffffffull ? 0xffffffffu : (uint32_t)c;
+  }
 }
 
-// one CTA: stable partition of the tile numbers into three classes (more than 3/4, more than 1/4 run positions, rest)
+// one CTA: stable partition of the tile numbers into four classes of estimated cost, the dearest first
+__device__ __forceinline__ uint32_t tile_class(uint32_t c)
+{
+  return c > 32 * kTile ? 0u : (c > 8 * kTile ? 1u : (c > kTile ? 2u : 3u));
+}
+
 __global__ void __launch_bounds__(256)
 k_tile_order(const uint32_t* cost, uint32_t n_tiles, uint32_t* order)
 {
@@ -322,22 +341,12 @@ k_tile_order(const uint32_t* cost, uint32_t n_tiles, uint32_t* order)
   const uint32_t per = (n_tiles + blockDim.x - 1) / blockDim.x;
   const uint32_t lo = min(threadIdx.x * per, n_tiles), hi = min(lo + per, n_tiles);
   uint32_t base = 0;
-  for (uint32_t cls = 0; cls < 3; cls++)
+  for (uint32_t cls = 0; cls < 4; cls++)
   {
     uint32_t mine = 0;
-    for (uint32_t i = lo; i < hi; i++)
-    {
-      const uint32_t c = cost[i];
-      const uint32_t k = c > 3 * kTile / 4 ? 0u : (c > kTile / 4 ? 1u : 2u);
-      mine += k == cls ? 1u : 0u;
-    }
+    for (uint32_t i = lo; i < hi; i++) mine += tile_class(cost[i]) == cls ? 1u : 0u;
     uint32_t at = base + block_excl_scan(mine, ws, &tot);
-    for (uint32_t i = lo; i < hi; i++)
-    {
-      const uint32_t c = cost[i];
-      const uint32_t k = c > 3 * kTile / 4 ? 0u : (c > kTile / 4 ? 1u : 2u);
-      if (k == cls) order[at++] = i;
-    }
+    for (uint32_t i = lo; i < hi; i++) if (tile_class(cost[i]) == cls) order[at++] = i;
     base += tot;
     __syncthreads();
   }
