@@ -749,6 +749,15 @@ int sz4_last_stats(const sz4_ctx* ctx, double* kernel_ms, unsigned long long* la
 
 long long sz4_last_dp_redos(const sz4_ctx* ctx) { return ctx ? (long long)ctx->dp_redos : -1; }
 /* debug: raw counters of the last batch (k-cycles): [2] longest spec task, total spec, its length; [4] verify per block max, redo max */
+#ifdef SZ4_TILE_STATS
+// debugging aid, only in builds with -DSZ4_TILE_STATS (tools/tile_stats.py)
+int sz4_debug_tile_stats(unsigned* us, unsigned* t0, unsigned n)
+{
+  if (cudaMemcpyFromSymbol(us, sz4::g_tile_us, n * 4) != cudaSuccess) return -1;
+  return cudaMemcpyFromSymbol(t0, sz4::g_tile_t0, n * 4) != cudaSuccess ? -1 : 0;
+}
+#endif
+
 const unsigned* sz4_debug_counters(const sz4_ctx* ctx) { return ctx ? (const unsigned*)(ctx->h_seg_total + 1) : nullptr; }
 long long sz4_last_path_redos(const sz4_ctx* ctx) { return ctx ? (long long)ctx->path_redos : -1; }
 

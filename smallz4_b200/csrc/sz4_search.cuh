@@ -352,6 +352,12 @@ k_tile_order(const uint32_t* cost, uint32_t n_tiles, uint32_t* order)
   }
 }
 
+#ifdef SZ4_TILE_STATS
+// debugging aid (tools/tile_stats.py): duration and start of every tile in microseconds
+__device__ uint32_t g_tile_us[1 << 16], g_tile_t0[1 << 16];
+__device__ __forceinline__ unsigned long long tile_clock() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#endif
+
 __global__ void __launch_bounds__(kSearchThreads, 1)
 k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, const uint32_t* run_fwd,
          const uint16_t* ones_back, uint32_t* mlen, uint16_t* mdist, uint32_t tiles_per_block, Geom g, int use_bulk,
@@ -362,6 +368,9 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
   __shared__ uint32_t next_pos;
 
   const uint32_t tile = tile_order != nullptr ? tile_order[blockIdx.x] : blockIdx.x;   // CTAs start in blockIdx order
+#ifdef SZ4_TILE_STATS
+  const unsigned long long tile_t0 = tile_clock();
+#endif
   const uint32_t j = tile / tiles_per_block;
   const uint32_t t = tile % tiles_per_block;
   const uint32_t t0 = block_begin(g, j) + t * kTile;
@@ -546,6 +555,10 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
     }
     idle = __ballot_sync(0xffffffffu, state == kIdle && !exhausted);
   }
+#ifdef SZ4_TILE_STATS
+  __syncthreads();
+  if (threadIdx.x == 0 && tile < (1u << 16)) { g_tile_us[tile] = (uint32_t)((tile_clock() - tile_t0) / 1000); g_tile_t0[tile] = (uint32_t)(tile_t0 / 1000); }
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------

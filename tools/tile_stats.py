@@ -1,5 +1,10 @@
 #!/usr/bin/env python
-"""Debugging aid (needs a library built with -DSZ4_TILE_STATS): duration of every k_search tile of one batch."""
+"""Debugging aid: duration of every k_search tile of one batch (how the tail of the kernel was found).
+
+    nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -shared -Xcompiler -fPIC -DSZ4_TILE_STATS \\
+         smallz4_b200/csrc/sz4_pipeline.cu -o variants/tilestats.so
+    SMALLZ4_B200_LIB=variants/tilestats.so python tools/tile_stats.py mixed 256
+"""
 import ctypes, os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
