@@ -328,10 +328,14 @@ k_tile_cost(const uint16_t* pe, uint32_t tiles_per_block, Geom g, uint32_t* cost
   }
 }
 
-// one CTA: stable partition of the tile numbers into four classes of estimated cost, the dearest first
+// one CTA: stable partition of the tile numbers into eight classes of estimated cost, the dearest first
 __device__ __forceinline__ uint32_t tile_class(uint32_t c)
 {
-  return c > 32 * kTile ? 0u : (c > 8 * kTile ? 1u : (c > kTile ? 2u : 3u));
+  // eight classes: more than 128, 64, 32, 16, 8, 4 tiles' worth, more than one (any run structure at all), the rest
+  const uint32_t x = c / kTile;
+  if (x >= 128) return 0u;
+  if (x >= 4) return 7u - (uint32_t)(31 - __clz((int)x));       // 64..127 -> 1, 32..63 -> 2, ..., 4..7 -> 5
+  return c > kTile ? 6u : 7u;
 }
 
 __global__ void __launch_bounds__(256)
@@ -341,7 +345,7 @@ k_tile_order(const uint32_t* cost, uint32_t n_tiles, uint32_t* order)
   const uint32_t per = (n_tiles + blockDim.x - 1) / blockDim.x;
   const uint32_t lo = min(threadIdx.x * per, n_tiles), hi = min(lo + per, n_tiles);
   uint32_t base = 0;
-  for (uint32_t cls = 0; cls < 4; cls++)
+  for (uint32_t cls = 0; cls < 8; cls++)
   {
     uint32_t mine = 0;
     for (uint32_t i = lo; i < hi; i++) mine += tile_class(cost[i]) == cls ? 1u : 0u;
