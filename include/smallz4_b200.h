@@ -54,7 +54,7 @@ const char* sz4_version(void);
    of 65536, >= 131072; 0 = format default), "stage_bulk" (1 = cp.async.bulk staging, 0 = plain loads),
    "debug_keep" (keep intermediates of the last batch for sz4_debug_fetch), "profile" (per-phase CUDA-event
    timing for sz4_last_phase_ms), "force_scalar" (tests: route a dictionary stream through the scalar finder);
-   match-finder scheduling, results never depend on them: "fast_hops" (candidates per lane and round, 1..64),
+   match-finder scheduling, results never depend on them: "fast_hops" (candidates per lane and round, 1..1024),
    "fast_lanes" (lanes that must still be walking for a round to go on, 0..32), "dense_a" / "dense_b" (positions
    whose first two chain hops add up to less than this go first / second; dense_a = 0: one pass) */
 int sz4_set_option(sz4_ctx* ctx, const char* name, long long value);

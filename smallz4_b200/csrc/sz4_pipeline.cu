@@ -55,7 +55,7 @@ struct sz4_ctx
   int      stage_bulk = 1;
   int      debug_keep = 0;
   int      force_scalar = 0;
-  uint32_t fast_hops = 32;     // k_search: at most this many candidates per lane and round in the fast loop ...
+  uint32_t fast_hops = 64;     // k_search: at most this many candidates per lane and round in the fast loop ...
   uint32_t dense_a = 256, dense_b = 2048;   // k_search: first-two-hops distance below which a position goes in the first / second pass (0 = one pass)
   uint32_t fast_lanes = 8;     // ... which goes on in steps of eight while at least this many lanes are still walking
   // device memory (grow-only)
@@ -622,7 +622,7 @@ int sz4_set_option(sz4_ctx* ctx, const char* name, long long value)
   if (!strcmp(name, "block_size")) { ctx->block_size_override = (uint32_t)value; return SZ4_OK; }
   if (!strcmp(name, "stage_bulk")) { ctx->stage_bulk = value != 0; return SZ4_OK; }
   if (!strcmp(name, "debug_keep")) { ctx->debug_keep = value != 0; return SZ4_OK; }
-  if (!strcmp(name, "fast_hops")) { if (value < 1 || value > 64) return SZ4_ERR_ARG; ctx->fast_hops = (uint32_t)value; return SZ4_OK; }
+  if (!strcmp(name, "fast_hops")) { if (value < 1 || value > 1024) return SZ4_ERR_ARG; ctx->fast_hops = (uint32_t)value; return SZ4_OK; }
   if (!strcmp(name, "dense_a")) { if (value < 0 || value > 65536) return SZ4_ERR_ARG; ctx->dense_a = (uint32_t)value; return SZ4_OK; }
   if (!strcmp(name, "dense_b")) { if (value < 0 || value > 65536) return SZ4_ERR_ARG; ctx->dense_b = (uint32_t)value; return SZ4_OK; }
   if (!strcmp(name, "fast_lanes")) { if (value < 0 || value > 32) return SZ4_ERR_ARG; ctx->fast_lanes = (uint32_t)value; return SZ4_OK; }
