@@ -77,10 +77,19 @@ int sz4_compress_host(sz4_ctx* ctx, const void* src, size_t n, void* dst, size_t
    start on a block border of the stream; is_stream_first / is_stream_last say whether the range
    contains the first / last block of the stream.  Writes the concatenated [size][payload] block
    records (no frame header, no end mark) to d_dst (device) and their total length to *segment_len.
-   This is the unit one GPU of a sharded job produces; blocks depend only on their 64 KiB halo. */
+   This is the unit one GPU of a sharded job produces; blocks depend only on their 64 KiB halo.
+   cuda_stream (a cudaStream_t, NULL = the default stream): work already enqueued there (e.g. the producer of
+   d_src) is waited for on the device; the call itself returns when the records are complete. */
 int sz4_compress_device(sz4_ctx* ctx, const void* d_src, size_t halo, size_t n, int is_stream_first, int is_stream_last,
                         void* d_dst, size_t dst_capacity, size_t* segment_len,
                         unsigned short max_chain_length, int use_legacy_format, void* cuda_stream);
+
+/* The same unit from and to HOST memory (pinned buffers make the copies asynchronous): src points at `halo` bytes of
+   history followed by `n` bytes of whole blocks; the block records go to dst (host).  What one rank of a sharded job
+   calls when its range of the input lives in host memory; the copies overlap the kernels batch by batch. */
+int sz4_compress_host_range(sz4_ctx* ctx, const void* src, size_t halo, size_t n, int is_stream_first, int is_stream_last,
+                            void* dst, size_t dst_capacity, size_t* segment_len,
+                            unsigned short max_chain_length, int use_legacy_format);
 
 /* frame header / end mark (smallz4.h:479-496, 809-813) for callers that assemble shards themselves */
 size_t sz4_frame_header(unsigned char* dst, int use_legacy_format);

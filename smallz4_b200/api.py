@@ -50,6 +50,8 @@ def load_library(path=None):
     lib.sz4_compress_host.restype = i32
     lib.sz4_compress_device.argtypes = [vp, vp, sz, sz, i32, i32, vp, sz, ctypes.POINTER(sz), ctypes.c_ushort, i32, vp]
     lib.sz4_compress_device.restype = i32
+    lib.sz4_compress_host_range.argtypes = [vp, vp, sz, sz, i32, i32, vp, sz, ctypes.POINTER(sz), ctypes.c_ushort, i32]
+    lib.sz4_compress_host_range.restype = i32
     lib.sz4_frame_header.argtypes = [vp, i32]; lib.sz4_frame_header.restype = sz
     lib.sz4_frame_end.argtypes = [vp, i32]; lib.sz4_frame_end.restype = sz
     lib.sz4_last_stats.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_ulonglong)]
@@ -124,6 +126,13 @@ class Compressor:
         out = ctypes.c_size_t(0)
         self._check(self.lib.sz4_compress_device(self.h, d_src_ptr, halo, n, int(first), int(last), d_dst_ptr, cap,
                                                  ctypes.byref(out), level_to_chain(level), int(use_legacy_format), stream))
+        return out.value
+
+    def compress_range_into(self, src_ptr, halo, n, dst_ptr, cap, level=9, first=False, last=True, use_legacy_format=False):
+        """Host pointers: `halo` bytes of history then `n` bytes of whole blocks in, block records out (host)."""
+        out = ctypes.c_size_t(0)
+        self._check(self.lib.sz4_compress_host_range(self.h, src_ptr, halo, n, int(first), int(last), dst_ptr, cap,
+                                                     ctypes.byref(out), level_to_chain(level), int(use_legacy_format)))
         return out.value
 
     def lz4(self, get_bytes, send_bytes, max_chain_length=MAX_CHAIN_LENGTH, dictionary=None, use_legacy_format=False):

@@ -44,7 +44,7 @@ struct sz4_ctx
   cudaStream_t stream = nullptr;
   cudaEvent_t  ev0 = nullptr, ev1 = nullptr;
   cudaStream_t copy_stream = nullptr;                 // input of the next batch / output of the previous one, next to the kernels
-  cudaEvent_t  ev_in = nullptr, ev_out[2] = { nullptr, nullptr };
+  cudaEvent_t  ev_in = nullptr, ev_out[2] = { nullptr, nullptr }, ev_user = nullptr;
   cudaEvent_t  pev[8] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
   double       phase_ms[7] = { 0, 0, 0, 0, 0, 0, 0 };   // sort, chain, search, fixup, dp, path, emit
   int          profile = 0;
@@ -579,6 +579,7 @@ int sz4_create(sz4_ctx** out, int device)
       cudaEventCreateWithFlags(&ctx->ev_in, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->ev_out[0], cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->ev_out[1], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_user, cudaEventDisableTiming) != cudaSuccess ||
       cudaMallocHost((void**)&ctx->h_seg_total, 64) != cudaSuccess)
   {
     fprintf(stderr, "smallz4_b200: cannot initialise CUDA device %d\n", device);
@@ -607,6 +608,7 @@ void sz4_destroy(sz4_ctx* ctx)
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   for (int k = 0; k < 8; k++) if (ctx->pev[k]) cudaEventDestroy(ctx->pev[k]);
   if (ctx->ev_in) cudaEventDestroy(ctx->ev_in);
+  if (ctx->ev_user) cudaEventDestroy(ctx->ev_user);
   for (int k = 0; k < 2; k++) if (ctx->ev_out[k]) cudaEventDestroy(ctx->ev_out[k]);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -704,13 +706,32 @@ int sz4_compress_device(sz4_ctx* ctx, const void* d_src, size_t halo, size_t n, 
 {
   if (!ctx || !d_src || !d_dst || !segment_len || max_chain == 0) return SZ4_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
-  (void)cuda_stream;   // work is ordered on the context's stream; the caller's stream is synchronised by the blocking return
+  // the caller's stream may still be producing d_src (or reading d_dst): the context's streams start behind it.
+  // The call returns after its own work has finished, so nothing has to be handed back to that stream.
+  CK(cudaEventRecord(ctx->ev_user, (cudaStream_t)cuda_stream));
+  CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_user, 0));
+  CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_user, 0));
   ctx->kernel_ms = 0; ctx->launches = 0; ctx->dp_redos = 0; ctx->path_redos = 0;
   for (int k = 0; k < 7; k++) ctx->phase_ms[k] = 0;
   StreamJob job;
   job.src = (const uint8_t*)d_src; job.src_on_device = true; job.halo_in_src = halo; job.n = n;
   job.first = is_first != 0; job.last = is_last != 0;
   job.dst = (uint8_t*)d_dst; job.dst_on_device = true; job.cap = cap; job.max_chain = max_chain; job.legacy = legacy != 0;
+  if (job.first && halo != 0) { ctx->err = "the first block of a stream has no halo"; return SZ4_ERR_ARG; }
+  return compress_blocks(ctx, job, segment_len);
+}
+
+int sz4_compress_host_range(sz4_ctx* ctx, const void* src, size_t halo, size_t n, int is_first, int is_last,
+                            void* dst, size_t cap, size_t* segment_len, unsigned short max_chain, int legacy)
+{
+  if (!ctx || !src || !dst || !segment_len || max_chain == 0) return SZ4_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  ctx->kernel_ms = 0; ctx->launches = 0; ctx->dp_redos = 0; ctx->path_redos = 0;
+  for (int k = 0; k < 7; k++) ctx->phase_ms[k] = 0;
+  StreamJob job;
+  job.src = (const uint8_t*)src; job.halo_in_src = halo; job.n = n;
+  job.first = is_first != 0; job.last = is_last != 0;
+  job.dst = (uint8_t*)dst; job.cap = cap; job.max_chain = max_chain; job.legacy = legacy != 0;
   if (job.first && halo != 0) { ctx->err = "the first block of a stream has no halo"; return SZ4_ERR_ARG; }
   return compress_blocks(ctx, job, segment_len);
 }

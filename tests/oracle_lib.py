@@ -125,3 +125,30 @@ def reference_compress(data, level=9, legacy=False, dictionary=None, max_chain=N
                                  dst.ctypes.data, cap)
     assert n >= 0
     return dst[:n].tobytes()
+
+
+def reference_cat():
+    """Path of the reference's own decoder (oracle/_ref/smallz4cat, built from /root/reference/smallz4cat.c), or None."""
+    exe = os.path.join(ORACLE_DIR, "_ref", "smallz4cat")
+    if not os.path.exists(exe) and os.path.exists("/root/reference/smallz4cat.c"):
+        build_oracle()
+    return exe if os.path.exists(exe) else None
+
+
+def reference_decompress(frame, dictionary=None):
+    """Decode with the UNMODIFIED smallz4cat: frame on stdin, output on stdout (smallz4cat.c:362-420; with -D the
+    file-name argument is not usable, so stdin it is)."""
+    exe = reference_cat()
+    assert exe is not None, "oracle/_ref/smallz4cat not built"
+    cmd = [exe]
+    tmp = None
+    if dictionary is not None and len(dictionary):
+        import tempfile
+        tmp = tempfile.NamedTemporaryFile(suffix=".dict")
+        tmp.write(bytes(dictionary)); tmp.flush()
+        cmd += ["-D", tmp.name]
+    r = subprocess.run(cmd, input=bytes(frame), capture_output=True)
+    if tmp is not None:
+        tmp.close()
+    assert r.returncode == 0, f"smallz4cat failed: {r.stderr[:200]!r}"
+    return r.stdout

@@ -81,29 +81,139 @@ def test_intermediates_match_oracle(gpu):
 
 
 def test_batches_are_independent(gpu):
-    """Blocks depend only on their 64 KiB halo: any batching gives the same frame."""
-    data = corpus.make("mixed", 40 << 20, seed=9).tobytes()
-    a = gpu.compress(data, level=6)
-    gpu.set_option("batch_blocks", 3)
-    try:
-        b = gpu.compress(data, level=6)
-    finally:
-        gpu.set_option("batch_blocks", 64)
-    assert a == b
-    assert oracle_decompress(a, len(data)) == data
+    """Blocks depend only on their 64 KiB halo: any batching gives the same frame, and it is the reference's
+    (the first ten blocks of the bench corpus against their golden digests, level 6 and level 9)."""
+    gb = _golden_blocks()
+    data = corpus.make(gb["kind"], 10 * gb["block"], gb["seed"])
+    for level in (6, 9):
+        a = gpu.compress(data, level=level)
+        gpu.set_option("batch_blocks", 3)
+        try:
+            b = gpu.compress(data, level=level)
+        finally:
+            gpu.set_option("batch_blocks", 64)
+        assert a == b
+        if str(level) in gb["levels"]:
+            _check_blocks(_block_records(b), level)
+    assert oracle_decompress(a, len(data)) == data.tobytes()
 
 
-def test_full_size_level9_properties(gpu):
-    """BASELINE configs[1]: 256 MB mixed corpus at -9.  The scalar reference needs hours for this, so
-    the full-size check uses properties: the frame decodes back to the input (smallz4cat restatement),
-    the first block equals the oracle's, and greedy level -1 of the same input is byte-identical."""
-    n = 256 << 20
-    data = corpus.make("mixed", n, seed=1)
-    frame = gpu.compress(data, level=9)
-    assert oracle_decompress(frame, n) == data.tobytes()
-    fast = gpu.compress(data, level=1)
-    want, _ = oracle_compress(data, 1)
-    assert fast == want
+def _golden_blocks():
+    path = os.path.join(os.path.dirname(__file__), "golden", "golden_blocks.json")
+    with open(path) as f:
+        return json.load(f)
+
+
+def _block_records(frame):
+    """The [size][payload] records of a modern frame (smallz4.h:769-780), header and end mark checked."""
+    assert frame[:7] == bytes([0x04, 0x22, 0x4D, 0x18, 0x40, 0x70, 0xDF])
+    at, out = 7, []
+    while True:
+        word = int.from_bytes(frame[at:at + 4], "little")
+        if word == 0:
+            break
+        out.append(frame[at:at + 4 + (word & 0x7FFFFFFF)])
+        at += 4 + (word & 0x7FFFFFFF)
+    assert at + 4 == len(frame)
+    return out
+
+
+@pytest.fixture(scope="module")
+def bench_corpus():
+    gb = _golden_blocks()
+    return corpus.make(gb["kind"], gb["size"], gb["seed"])
+
+
+def _check_blocks(records, level, first_block=0):
+    gold = _golden_blocks()["levels"][str(level)]
+    bad = [first_block + k for k, r in enumerate(records)
+           if len(r) != gold[first_block + k]["n"] or digest(r) != gold[first_block + k]["sha256"]]
+    assert not bad, f"level {level}: block records {bad} differ from the unmodified reference"
+
+
+@pytest.mark.parametrize("level", [9, 8, 7, 6, 5, 4, 3, 2, 1])
+def test_full_size_every_block_matches_reference(gpu, bench_corpus, level):
+    """BASELINE configs[1] and [2]: the 256 MB mixed corpus at every level, all 64 block records against digests of
+    the UNMODIFIED reference (tests/golden/make_golden_blocks.py), and the frame through the reference's own decoder."""
+    gb = _golden_blocks()
+    if str(level) not in gb["levels"]:
+        pytest.skip(f"no golden block digests for level {level}")
+    frame = gpu.compress(bench_corpus, level=level)
+    records = _block_records(frame)
+    assert len(records) == gb["size"] // gb["block"]
+    _check_blocks(records, level)
+    if level in (9, 1):
+        from oracle_lib import reference_decompress, reference_cat
+        if reference_cat() is not None:
+            assert reference_decompress(frame) == bench_corpus.tobytes()      # smallz4cat.c:112-360, the real one
+        assert oracle_decompress(frame, gb["size"]) == bench_corpus.tobytes()
+
+
+@pytest.mark.parametrize("world", [2, 5, 8])
+def test_sharded_device_path_matches_reference(gpu, bench_corpus, world):
+    """BASELINE configs[3], correctness half: the stream cut into `world` ranges of whole blocks with their halos
+    (smallz4_b200/shard.py), each compressed by sz4_compress_device on its own, gives the reference's block records
+    (64 golden digests at -9) and the same frame as the single-stream call."""
+    import torch
+    from smallz4_b200 import shard
+    gb = _golden_blocks()
+    if "9" not in gb["levels"]:
+        pytest.skip("no golden block digests for level 9")
+    total = gb["size"]
+    dev = torch.device("cuda", 0)
+    records, at = [], 0
+    for begin, end in shard.plan(total, world):
+        halo = shard.halo_for(begin)
+        d_in = torch.from_numpy(bench_corpus[begin - halo:end]).to(dev)
+        cap = (end - begin) + 4 * ((end - begin) // shard.BLOCK + 2) + 4096
+        d_out = torch.empty(cap, dtype=torch.uint8, device=dev)
+        n = shard.compress_shard(gpu, d_in.data_ptr(), halo, end - begin, d_out.data_ptr(), cap, 9,
+                                 first=(begin == 0), last=(end == total))
+        body = d_out[:n].cpu().numpy().tobytes()
+        recs = _block_records(shard.frame_header() + body + shard.frame_end())
+        _check_blocks(recs, 9, first_block=begin // shard.BLOCK)
+        records += recs
+        at += 1
+    assert len(records) == total // gb["block"]
+
+
+@pytest.mark.parametrize("level,legacy", [(3, False), (6, False), (5, True)])
+def test_sharded_device_path_ragged_tail(gpu, level, legacy):
+    """Shards whose last range ends mid-block, at levels the oracle finishes quickly: sharded == single stream == oracle."""
+    import torch
+    from smallz4_b200 import shard
+    total = (44 << 20) + 12345
+    data = corpus.make("mixed", total, seed=23)
+    want, _ = oracle_compress(data, level, legacy)
+    assert gpu.compress(data, level=level, use_legacy_format=legacy) == want
+    dev = torch.device("cuda", 0)
+    block = shard.BLOCK_LEGACY if legacy else shard.BLOCK
+    for world in (3, 4):
+        body = b""
+        for begin, end in shard.plan(total, world, block=block):
+            if end == begin:
+                continue
+            halo = shard.halo_for(begin, legacy)
+            d_in = torch.from_numpy(data[begin - halo:end]).to(dev)
+            cap = 2 * (end - begin) + 4096
+            d_out = torch.empty(cap, dtype=torch.uint8, device=dev)
+            n = shard.compress_shard(gpu, d_in.data_ptr(), halo, end - begin, d_out.data_ptr(), cap, level,
+                                     first=(begin == 0), last=(end == total), legacy=legacy)
+            body += d_out[:n].cpu().numpy().tobytes()
+        assert shard.frame_header(legacy) + body + shard.frame_end(legacy) == want
+
+
+def test_round_trip_through_the_reference_decoder(gpu):
+    """Every kind of frame the path produces decodes with the reference's own smallz4cat (stdin -> stdout)."""
+    from oracle_lib import reference_cat, reference_decompress
+    if reference_cat() is None:
+        pytest.skip("oracle/_ref/smallz4cat not built")
+    for kind, n, level, legacy in [("text", 3_000_000, 9, False), ("mixed", 9_000_000, 9, False), ("runs", 1_000_000, 5, False),
+                                   ("random", 4_200_000, 9, False), ("zeros", 5_000_000, 9, False), ("binary", 2_000_000, 2, True),
+                                   ("text", 1_000_000, 0, False)]:
+        data = corpus.make(kind, n, seed=41).tobytes()
+        frame = gpu.compress(data, level=level, use_legacy_format=legacy)
+        assert reference_decompress(frame) == data, (kind, n, level, legacy)
 
 
 def test_lz4_callback_api(gpu):

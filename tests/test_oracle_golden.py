@@ -61,3 +61,49 @@ def test_reference_dictionary_frames_do_not_round_trip():
     except AssertionError:
         back = None
     assert back != data
+
+
+# ---------------------------------------------------------------------------------------------
+# The decoder restatement (oracle/lz4cat_oracle.c) against the reference's own smallz4cat
+# (oracle/_ref/smallz4cat, compiled from /root/reference/smallz4cat.c by oracle/Makefile).
+# ---------------------------------------------------------------------------------------------
+def _cat_cases():
+    return [c for c in CASES if not c["dict"] and not (c["legacy"] and c["level"] == 0) and c["size"] <= 400_000
+            and c["level"] in (0, 1, 4, 9)]
+
+
+def test_decoder_restatement_is_pinned_to_the_reference_decoder():
+    """Every golden frame decodes to the same bytes with the real smallz4cat and with the restatement, and
+    both give the input back (smallz4cat.c:112-360)."""
+    from oracle_lib import reference_cat, reference_decompress
+    if reference_cat() is None:
+        pytest.skip("oracle/_ref/smallz4cat not built (no /root/reference here)")
+    n = 0
+    for c in _cat_cases():
+        data = case_input(c)
+        frame, _ = oracle_compress(data, c["level"], c["legacy"])
+        assert digest(frame) == c["sha256"]
+        real = reference_decompress(frame)
+        assert real == data, case_id(c)
+        assert oracle_decompress(frame, len(data)) == real, case_id(c)
+        n += 1
+    assert n >= 40
+
+
+def test_reference_decoder_rejects_what_the_restatement_rejects():
+    """A truncated frame: neither decoder returns the input."""
+    from oracle_lib import reference_cat
+    import subprocess
+    if reference_cat() is None:
+        pytest.skip("oracle/_ref/smallz4cat not built")
+    c = next(c for c in CASES if c["kind"] == "text" and c["size"] == 300_000 and c["level"] == 9)
+    data = case_input(c)
+    frame, _ = oracle_compress(data, 9)
+    cut = frame[: len(frame) // 2]
+    r = subprocess.run([reference_cat()], input=cut, capture_output=True)
+    assert r.stdout != data
+    try:
+        back = oracle_decompress(cut, len(data))
+    except AssertionError:
+        back = None
+    assert back != data
