@@ -169,7 +169,7 @@ class Compressor:
         return self.lib.sz4_last_path_redos(self.h)
 
     def debug_fetch(self, what, count):
-        dt = {"pe": np.uint16, "ph": np.uint16, "len_found": np.uint32, "dist_found": np.uint16,
+        dt = {"pe": np.uint16, "ph": np.uint16, "pe8": np.uint16, "jump": np.uint64, "len_found": np.uint32, "dist_found": np.uint16,
               "len_final": np.uint32, "dist_final": np.uint16, "cost": np.uint32}[what]
         out = np.zeros(count, dtype=dt)
         self._check(self.lib.sz4_debug_fetch(self.h, what.encode(), out.ctypes.data, count))

@@ -1,0 +1,325 @@
+// sz4_lsd.cuh -- phase 1 without a dictionary: prefix-class tables for every position, from ONE byte-wise LSD radix sort.
+//
+// What the reference builds (smallz4.h:645-720) is, per position, the distance to the previous position that starts
+// with the same four bytes (previousExact); findLongestMatch (smallz4.h:173-255) then walks that chain and keeps every
+// strictly longer candidate.  A candidate can only be longer than a match of L bytes if it shares the first L+1 bytes,
+// so the candidates the walk actually keeps are: the nearest position with the same 4 bytes, then the nearest with the
+// same (L1+1) bytes, and so on.  With the distance to the previous position of the same K-byte prefix for K = 4..8
+// ("pe4" .. "pe8") the match finder jumps from keeper to keeper and only walks a chain -- the 8-byte one -- once the
+// match is at least 8 bytes long (sz4_search.cuh).  On the mixed corpus this visits 25 candidates per position instead
+// of 170.
+//
+// All five tables fall out of one sort.  Element "anchor a" is sorted by the bytes in FRONT of it, nearest first:
+// pass j (1..8) is a stable counting sort by data[a - j].  After pass j the elements are ordered by the string
+// data[a-j .. a-1], ties by a -- that is, positions p = a - j are grouped by their j-byte prefix, each group in
+// position order, so the previous position with the same j-byte prefix is simply the left neighbour.  Passes 5..8 read
+// the order of passes 4..7 anyway and pick up pe4..pe7 on the way (carried along in `car`); k_lsd_extract reads the
+// final order for pe8 and writes the tables out by position.
+//
+// A pass is one kernel: global digit offsets come from a byte histogram of the input (the digits of pass j are the
+// input bytes shifted by j), the rank of a tile inside its digits from a decoupled look-back over the tiles in front
+// of it (each tile publishes its digit counts, then the running sums), and the tile is put in digit order in shared
+// memory before it is written, so that a warp's store covers a few long pieces.  HBM-bound: 24-40 B per element and pass.
+#pragma once
+#include "sz4_device.cuh"
+#include "sz4_sort.cuh"
+
+namespace sz4
+{
+enum : uint32_t
+{
+  kLsdThreads = 256,
+  kLsdItems   = 16,
+  kLsdTile    = kLsdThreads * kLsdItems,   // 4096 elements per CTA
+  kLsdBins    = 256,
+  kLsdPasses  = 8,
+  kLsdSpin    = 1u << 24                   // polls of one look-back slot before the kernel gives up (never in practice)
+};
+
+struct LsdBuf
+{
+  uint64_t* key;    // data[a-8 .. a-1], data[a-1] in the low byte
+  uint32_t* pos;    // a
+  uint64_t* car;    // pe4[a-4] | pe5[a-5] << 16 | pe6[a-6] << 32 | pe7[a-7] << 48, as far as known
+};
+
+__device__ __forceinline__ uint64_t lsd_key(const uint8_t* data, uint32_t a)
+{
+  // the eight bytes in front of a, first byte in memory most significant
+  const uintptr_t at = (uintptr_t)(data + a) - 8;
+  const uint64_t* w = (const uint64_t*)(at & ~(uintptr_t)7);
+  const uint32_t sh = (uint32_t)(at & 7) * 8;
+  const uint64_t lo = w[0];
+  const uint64_t v = sh ? (lo >> sh) | (w[1] << (64 - sh)) : lo;
+  const uint32_t a0 = __byte_perm((uint32_t)v, 0, 0x0123), a1 = __byte_perm((uint32_t)(v >> 32), 0, 0x0123);
+  return ((uint64_t)a0 << 32) | a1;
+}
+
+// ---- digit histograms: hist[v] = number of x in [lo, hi) with data[x] == v (the part all passes have in common).
+// Indices are signed: the first anchors look at the zero padding in front of the batch.
+__global__ void __launch_bounds__(256)
+k_lsd_hist(const uint8_t* data, int32_t lo, int32_t hi, uint32_t* hist)
+{
+  __shared__ uint32_t h[kLsdBins];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  // 16 aligned bytes per thread and step; equal neighbours are counted in a register first (runs of one byte would
+  // otherwise serialise on one counter)
+  const int32_t lo16 = lo & ~15;
+  const uint32_t steps = hi > lo16 ? (uint32_t)(hi - lo16 + 15) / 16 : 0;
+  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < steps; s += gridDim.x * blockDim.x)
+  {
+    const int32_t x0 = lo16 + (int32_t)(s * 16);
+    const uint4 q = *(const uint4*)(data + x0);
+    const uint32_t w[4] = { q.x, q.y, q.z, q.w };
+    uint32_t last = 0, cnt = 0;
+#pragma unroll
+    for (int32_t k = 0; k < 16; k++)
+    {
+      const int32_t x = x0 + k;
+      if (x < lo || x >= hi) continue;
+      const uint32_t b = (w[k >> 2] >> ((k & 3) * 8)) & 255u;
+      if (cnt != 0 && b == last) cnt++;
+      else { if (cnt) atomicAdd(&h[last], cnt); last = b; cnt = 1; }
+    }
+    if (cnt) atomicAdd(&h[last], cnt);
+  }
+  __syncthreads();
+  if (h[threadIdx.x]) atomicAdd(&hist[threadIdx.x], h[threadIdx.x]);
+}
+
+// one CTA of 256 threads: bases[j-1][v] = number of anchors in [a0, a1) whose digit of pass j (data[a-j]) is below v.
+// common = histogram of data[clo, chi); pass j looks at data[a0-j, a1-j) = j-1 more bytes in front and 8-j behind.
+__global__ void __launch_bounds__(256)
+k_lsd_bases(const uint8_t* data, int32_t a0, int32_t a1, int32_t clo, int32_t chi, const uint32_t* common, uint32_t* bases)
+{
+  __shared__ uint32_t ws[32], tot;
+  for (int32_t j = 1; j <= (int32_t)kLsdPasses; j++)
+  {
+    uint32_t c = common[threadIdx.x];
+    for (int32_t x = a0 - j; x < min(clo, a1 - j); x++) if (data[x] == threadIdx.x) c++;
+    for (int32_t x = max(chi, a0 - j); x < a1 - j; x++) if (data[x] == threadIdx.x) c++;
+    const uint32_t e = block_excl_scan(c, ws, &tot);
+    bases[(j - 1) * kLsdBins + threadIdx.x] = e;
+  }
+}
+
+// ---- decoupled look-back (one 64-bit word per tile and digit: status | pass tag | value)
+__device__ __forceinline__ uint64_t lsd_word(uint32_t status, uint32_t tag, uint32_t value)
+{
+  return ((uint64_t)status << 62) | ((uint64_t)tag << 56) | value;
+}
+__device__ __forceinline__ uint64_t lsd_peek(const uint64_t* p)
+{
+#ifdef SZ4_EMU
+  return *p;
+#else
+  uint64_t v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+#endif
+}
+__device__ __forceinline__ void lsd_post(uint64_t* p, uint64_t v)
+{
+#ifdef SZ4_EMU
+  *p = v;
+#else
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+#endif
+}
+
+// kFirst: pass 1, elements are made from the data.  kCar: the input has a `car` array (passes 6..8).
+// level: 0, or the prefix length whose table is read off the input order (passes 5..8: 4..7).
+template <bool kFirst, bool kCar>
+__global__ void __launch_bounds__(kLsdThreads)
+k_lsd_pass(LsdBuf in, LsdBuf out, const uint8_t* data, uint32_t a0, uint32_t n, uint32_t pass, uint32_t level, uint32_t first,
+           const uint32_t* bases, uint64_t* tile_state, uint32_t* tile_counter, uint32_t* err)
+{
+  __shared__ uint32_t cnt[kLsdThreads / 32][kLsdBins];
+  __shared__ uint32_t lstart[kLsdBins], gbase[kLsdBins];
+  __shared__ uint64_t stage[kLsdTile];
+  __shared__ uint8_t sdig[kLsdTile];
+  __shared__ uint32_t s_tile;
+
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);       // tiles are handed out in starting order: a tile only
+  for (uint32_t k = threadIdx.x; k < (kLsdThreads / 32) * kLsdBins; k += kLsdThreads) (&cnt[0][0])[k] = 0;   // waits for running ones
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  const uint32_t tile_base = tile * kLsdTile;
+  if (tile_base >= n) return;
+  const uint32_t tile_n = min((uint32_t)kLsdTile, n - tile_base);
+  const uint32_t shift = (pass - 1) * 8;
+
+  // ---- load: warp w owns elements [w*512, (w+1)*512) of the tile, as 16 rows of 32 in order
+  const uint32_t wbase = tile_base + warp * (32 * kLsdItems);
+  uint64_t key[kLsdItems], car[kLsdItems];
+  uint32_t pos[kLsdItems], rank[kLsdItems];
+#pragma unroll
+  for (uint32_t r = 0; r < kLsdItems; r++)
+  {
+    const uint32_t i = wbase + r * 32 + lane;
+    const bool valid = i < n;
+    if (kFirst) { pos[r] = a0 + i; key[r] = valid ? lsd_key(data, a0 + i) : 0; }
+    else { pos[r] = valid ? in.pos[i] : 0; key[r] = valid ? in.key[i] : 0; }
+    car[r] = (kCar && valid) ? in.car[i] : 0;
+  }
+  // ---- table of the input order: the left neighbour is the previous position with the same `level`-byte prefix
+  if (level != 0)
+  {
+    uint64_t pk = 0; uint32_t pp = 0;                               // element in front of the warp's first one
+    if (wbase > 0 && wbase < n && lane == 0) { pk = in.key[wbase - 1]; pp = in.pos[wbase - 1]; }
+    const uint32_t keep = 64 - 8 * level;
+#pragma unroll
+    for (uint32_t r = 0; r < kLsdItems; r++)
+    {
+      uint64_t lk = __shfl_up_sync(0xffffffffu, key[r], 1);
+      uint32_t lp = __shfl_up_sync(0xffffffffu, pos[r], 1);
+      if (lane == 0) { lk = pk; lp = pp; }
+      const uint32_t i = wbase + r * 32 + lane;
+      const uint32_t d = pos[r] - lp;
+      // both positions (anchor - level) must be ones the reference inserts (>= first)
+      const bool hit = i < n && i > 0 && ((key[r] ^ lk) << keep) == 0 && d <= kWindow && lp >= first + level;
+      if (hit) car[r] |= (uint64_t)d << (16 * (level - 4));
+      pk = __shfl_sync(0xffffffffu, key[r], 31);
+      pp = __shfl_sync(0xffffffffu, pos[r], 31);
+    }
+  }
+  // ---- rank inside the warp: __match_any_sync ranks equal digits inside a row, per-warp counters rank rows
+#pragma unroll
+  for (uint32_t r = 0; r < kLsdItems; r++)
+  {
+    const uint32_t i = wbase + r * 32 + lane;
+    const bool valid = i < n;
+    const uint32_t digit = valid ? (uint32_t)(key[r] >> shift) & 255u : 0xffffffffu;
+    const uint32_t peers = __match_any_sync(0xffffffffu, digit);
+    const uint32_t leader = (uint32_t)__ffs((int)peers) - 1;
+    const uint32_t before = (uint32_t)__popc(peers & ((1u << lane) - 1));
+    uint32_t start = 0;
+    if (valid && lane == leader)
+    {
+      start = cnt[warp][digit];
+      cnt[warp][digit] = start + (uint32_t)__popc(peers);
+    }
+    start = __shfl_sync(0xffffffffu, start, (int)leader);
+    rank[r] = start + before;
+    __syncwarp();
+  }
+  __syncthreads();
+  // ---- per digit (one thread each): rank of the warps, the tile's count, and the look-back over the tiles in front
+  {
+    const uint32_t d = threadIdx.x;
+    uint32_t run = 0;
+#pragma unroll
+    for (uint32_t w = 0; w < kLsdThreads / 32; w++)
+    {
+      const uint32_t c = cnt[w][d];
+      cnt[w][d] = run;
+      run += c;
+    }
+    lstart[d] = run;                                                // for now: this digit's count in the tile
+    uint64_t* mine = tile_state + (size_t)tile * kLsdBins + d;
+    uint32_t excl = 0;
+    if (tile == 0) lsd_post(mine, lsd_word(2, pass, run));
+    else
+    {
+      lsd_post(mine, lsd_word(1, pass, run));
+      for (uint32_t t = tile; t-- > 0; )
+      {
+        const uint64_t* there = tile_state + (size_t)t * kLsdBins + d;
+        uint64_t s = lsd_peek(there);
+        uint32_t spins = 0;
+        while ((uint32_t)((s >> 56) & 63u) != pass || (s >> 62) == 0)
+        {
+          if (++spins > kLsdSpin) { *err = 1; break; }              // a tile in front never published: do not hang the GPU
+          s = lsd_peek(there);
+        }
+        excl += (uint32_t)s;
+        if ((s >> 62) == 2 || spins > kLsdSpin) break;
+      }
+      lsd_post(mine, lsd_word(2, pass, excl + run));
+    }
+    gbase[d] = bases[(pass - 1) * kLsdBins + d] + excl;
+  }
+  __syncthreads();
+  if (warp == 0)
+  {
+    // exclusive scan of the 256 counts: eight per lane
+    uint32_t c[kLsdBins / 32], sum = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < kLsdBins / 32; k++) { c[k] = lstart[lane * (kLsdBins / 32) + k]; sum += c[k]; }
+    const uint32_t incl = warp_incl_scan(sum, lane);
+    uint32_t run = incl - sum;
+#pragma unroll
+    for (uint32_t k = 0; k < kLsdBins / 32; k++) { lstart[lane * (kLsdBins / 32) + k] = run; run += c[k]; }
+  }
+  __syncthreads();
+  // ---- the tile in digit order in shared memory, then out with consecutive threads on consecutive addresses
+  uint32_t slot[kLsdItems];
+#pragma unroll
+  for (uint32_t r = 0; r < kLsdItems; r++)
+  {
+    const uint32_t i = wbase + r * 32 + lane;
+    slot[r] = 0xffffffffu;
+    if (i < n)
+    {
+      const uint32_t digit = (uint32_t)(key[r] >> shift) & 255u;
+      slot[r] = lstart[digit] + cnt[warp][digit] + rank[r];
+      stage[slot[r]] = key[r];
+      sdig[slot[r]] = (uint8_t)digit;
+    }
+  }
+  __syncthreads();
+  uint32_t dst[kLsdItems];
+#pragma unroll
+  for (uint32_t m = 0; m < kLsdItems; m++)
+  {
+    const uint32_t k = m * kLsdThreads + threadIdx.x;
+    dst[m] = 0xffffffffu;
+    if (k < tile_n)
+    {
+      const uint32_t digit = sdig[k];
+      dst[m] = gbase[digit] + (k - lstart[digit]);
+      out.key[dst[m]] = stage[k];
+    }
+  }
+  __syncthreads();
+  uint32_t* stage32 = (uint32_t*)stage;
+#pragma unroll
+  for (uint32_t r = 0; r < kLsdItems; r++) if (slot[r] != 0xffffffffu) stage32[slot[r]] = pos[r];
+  __syncthreads();
+#pragma unroll
+  for (uint32_t m = 0; m < kLsdItems; m++) if (dst[m] != 0xffffffffu) out.pos[dst[m]] = stage32[m * kLsdThreads + threadIdx.x];
+  if (level != 0 || kCar)
+  {
+    __syncthreads();
+#pragma unroll
+    for (uint32_t r = 0; r < kLsdItems; r++) if (slot[r] != 0xffffffffu) stage[slot[r]] = car[r];
+    __syncthreads();
+#pragma unroll
+    for (uint32_t m = 0; m < kLsdItems; m++) if (dst[m] != 0xffffffffu) out.car[dst[m]] = stage[m * kLsdThreads + threadIdx.x];
+  }
+}
+
+// The final order (all eight bytes): pe8 from the left neighbour, and the tables out by position:
+//   jump[a] = { pe4[a-4], pe5[a-5], pe6[a-6], pe7[a-7] }  (8 bytes per anchor),  pe8[a-8]  (its own array: the match
+//   finder stages a 64 KiB window of it in shared memory).
+__global__ void __launch_bounds__(256)
+k_lsd_extract(LsdBuf in, uint32_t n, uint32_t first, uint64_t* jump, uint16_t* pe8)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t lane = threadIdx.x & 31;
+  const bool valid = i < n;
+  const uint64_t key = valid ? in.key[i] : 0;
+  const uint32_t pos = valid ? in.pos[i] : 0;
+  uint64_t lk = __shfl_up_sync(0xffffffffu, key, 1);
+  uint32_t lp = __shfl_up_sync(0xffffffffu, pos, 1);
+  if (lane == 0 && valid && i > 0) { lk = in.key[i - 1]; lp = in.pos[i - 1]; }
+  if (!valid) return;
+  const uint32_t d = pos - lp;
+  const bool hit = i > 0 && key == lk && d <= kWindow && lp >= first + 8;
+  jump[pos] = in.car[i];
+  if (pos >= first + 8) pe8[pos - 8] = hit ? (uint16_t)d : (uint16_t)0;
+}
+
+}  // namespace sz4

@@ -8,6 +8,7 @@
 #include "sz4_platform.h"
 #include "sz4_device.cuh"
 #include "sz4_sort.cuh"
+#include "sz4_lsd.cuh"
 #include "sz4_chain.cuh"
 #include "sz4_runs.cuh"
 #include "sz4_search.cuh"
@@ -55,10 +56,12 @@ struct sz4_ctx
   int      stage_bulk = 1;
   int      debug_keep = 0;
   int      force_scalar = 0;
+  int      debug_stop = 0;     // tests: 1 = stop behind phase 1 (the tables stay for sz4_debug_fetch)
   uint32_t fast_hops = 64;     // k_search: at most this many candidates per lane and round in the fast loop ...
   uint32_t dense_a = 256, dense_b = 2048;   // k_search: first-two-hops distance below which a position goes in the first / second pass (0 = one pass)
   uint32_t fast_lanes = 8;     // ... which goes on in steps of eight while at least this many lanes are still walking
   // device memory (grow-only)
+  DevBuf jump, lsd_state, lsd_misc, dbg_pe;              // sz4_lsd.cuh: pe4..pe7 by anchor, look-back words, histograms / counters
   DevBuf greedy_segs;                                  // k_greedy_*: entry / leave of every segment, and the number of second walks
   DevBuf dp_order;                                     // k_dp_spec: its tasks in starting order
   DevBuf tile_order;                                   // k_search: run positions per tile, and the tiles in starting order
@@ -134,7 +137,10 @@ static int run_batch(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
   RSV(pe, ((size_t)N + 2 * kPad) * 2);
   RSV(mlen, ((size_t)N + kPad) * 4);
   RSV(mdist, ((size_t)N + kPad) * 2);
-  RSV(scratch, ((size_t)N + kPad) * 16 + 256);
+  // the cost DP's four arrays; before that the ping-pong buffers of the sort (8-byte elements with a dictionary, else
+  // key + position + carried tables = 20 bytes per anchor, twice)
+  const size_t lsd_n = (size_t)N + 5 - g.first_ins, lsd_stride = (lsd_n + 63) & ~(size_t)63;
+  RSV(scratch, ((size_t)N + kPad) * 16 + 256 > 2 * 20 * lsd_stride ? ((size_t)N + kPad) * 16 + 256 : 2 * 20 * lsd_stride);
   RSV(saved_ph, (size_t)g.n_blocks * 4 + 64);
   RSV(saved_pe, (size_t)g.n_blocks * 4 + 64);
   RSV(seq_count, (size_t)g.n_blocks * 4 + 64);
@@ -158,6 +164,7 @@ static int run_batch(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
   uint32_t* saved_ph = (uint32_t*)ctx->saved_ph.p;
   uint32_t* saved_pe = (uint32_t*)ctx->saved_pe.p;
 
+  ctx->h_seg_total[7] = 0;                                         // error flag of the sort's look-back
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
   CK(cudaMemsetAsync(ctx->ph.p, 0, ((size_t)N + 2 * kPad) * 2, ctx->stream));
   CK(cudaMemsetAsync(ctx->pe.p, 0, ((size_t)N + 2 * kPad) * 2, ctx->stream));
@@ -176,50 +183,95 @@ static int run_batch(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
   }
   else
   {
-    // ---- phase 1: previous occurrence of every position's hash (sort) and exact chains
+    // ---- phase 1: the chains.  Without a dictionary: prefix-class tables pe4..pe8 from one byte-wise LSD sort
+    // (sz4_lsd.cuh).  With one: previousHash by a sort on the hash, then the reference's walk over the shifted ring.
     const uint32_t first = g.first_ins;
     const uint32_t count = N >= first + 4 ? N - 3 - first : 0;
+    const bool jump_tables = g.shift == 0;
     if (count > 0)
     {
-      uint64_t* bufA = (uint64_t*)ctx->scratch.p;
-      uint64_t* bufB = bufA + (((size_t)N + kPad + 1) & ~(size_t)1);
-      const uint32_t tiles = div_up(count, kSortTile);
-      const uint32_t hist_n = tiles * kSortBins;
-      RSV(hist, (size_t)hist_n * 4 + 64);
-      RSV(hist_scanned, (size_t)hist_n * 4 + 64);
-      uint32_t* hist = (uint32_t*)ctx->hist.p;
-      uint32_t* hscan = (uint32_t*)ctx->hist_scanned.p;
-      const uint32_t shifts[3] = { 0, 7, 14 }, masks[3] = { 127, 127, 63 };
-      uint64_t* src = nullptr;
-      uint64_t* dst = bufA;
-      for (int pass = 0; pass < 3; pass++)
+      if (jump_tables)
       {
-        if (pass == 0)
-          LAUNCH(ctx, k_sort_hist<true>, tiles, kSortThreads, 0, (const uint64_t*)nullptr, (const uint8_t*)data, first, count, shifts[0], masks[0], hist, tiles);
-        else
-          LAUNCH(ctx, k_sort_hist<false>, tiles, kSortThreads, 0, (const uint64_t*)src, (const uint8_t*)data, first, count, shifts[pass], masks[pass], hist, tiles);
-        int r = device_scan(ctx, hist, hscan, hist_n);
-        if (r != SZ4_OK) return r;
-        if (pass == 0)
-          LAUNCH(ctx, k_sort_scatter<true>, tiles, kSortThreads, 0, (const uint64_t*)nullptr, dst, (const uint8_t*)data, first, count, shifts[0], masks[0], (const uint32_t*)hscan, tiles);
-        else
-          LAUNCH(ctx, k_sort_scatter<false>, tiles, kSortThreads, 0, (const uint64_t*)src, dst, (const uint8_t*)data, first, count, shifts[pass], masks[pass], (const uint32_t*)hscan, tiles);
-        src = dst;
-        dst = (dst == bufA) ? bufB : bufA;
+        const uint32_t n = (uint32_t)lsd_n;                           // anchors first .. N+4
+        const uint32_t tiles = div_up(n, kLsdTile);
+        RSV(lsd_state, (size_t)tiles * kLsdBins * 8 + 64);
+        RSV(lsd_misc, (kLsdBins + kLsdPasses * kLsdBins + 64) * 4);
+        RSV(jump, ((size_t)N + 64) * 8);
+        uint32_t* common = (uint32_t*)ctx->lsd_misc.p;
+        uint32_t* bases = common + kLsdBins;
+        uint32_t* counters = bases + kLsdPasses * kLsdBins;           // [0..7] tile counters, [8] error flag
+        LsdBuf A, B;
+        A.key = (uint64_t*)ctx->scratch.p; A.car = A.key + lsd_stride; A.pos = (uint32_t*)(A.car + lsd_stride);
+        B.key = (uint64_t*)(A.pos + lsd_stride); B.car = B.key + lsd_stride; B.pos = (uint32_t*)(B.car + lsd_stride);
+        CK(cudaMemsetAsync(ctx->lsd_misc.p, 0, (kLsdBins + kLsdPasses * kLsdBins + 64) * 4, ctx->stream));
+        CK(cudaMemsetAsync(ctx->lsd_state.p, 0, (size_t)tiles * kLsdBins * 8, ctx->stream));
+        const int32_t a0 = (int32_t)first, a1 = (int32_t)(first + n);
+        const int32_t clo = a0 - 1, chi = a1 - 8 > clo ? a1 - 8 : clo;
+        LAUNCH(ctx, k_lsd_hist, 148 * 8, 256, 0, (const uint8_t*)data, clo, chi, common);
+        LAUNCH(ctx, k_lsd_bases, 1, 256, 0, (const uint8_t*)data, a0, a1, clo, chi, (const uint32_t*)common, bases);
+        LsdBuf src = A, dst = A;
+        for (uint32_t pass = 1; pass <= kLsdPasses; pass++)
+        {
+          const uint32_t level = pass >= 5 ? pass - 1 : 0;             // passes 5..8 read pe4..pe7 off their input order
+          if (pass == 1)
+            LAUNCH(ctx, (k_lsd_pass<true, false>), tiles, kLsdThreads, 0, src, dst, (const uint8_t*)data, first, n, pass, level, first,
+                   (const uint32_t*)bases, (uint64_t*)ctx->lsd_state.p, counters + (pass - 1), counters + 8);
+          else if (pass <= 5)
+            LAUNCH(ctx, (k_lsd_pass<false, false>), tiles, kLsdThreads, 0, src, dst, (const uint8_t*)data, first, n, pass, level, first,
+                   (const uint32_t*)bases, (uint64_t*)ctx->lsd_state.p, counters + (pass - 1), counters + 8);
+          else
+            LAUNCH(ctx, (k_lsd_pass<false, true>), tiles, kLsdThreads, 0, src, dst, (const uint8_t*)data, first, n, pass, level, first,
+                   (const uint32_t*)bases, (uint64_t*)ctx->lsd_state.p, counters + (pass - 1), counters + 8);
+          src = dst;
+          dst = (dst.key == A.key) ? B : A;
+        }
+        PHASE(1);
+        LAUNCH(ctx, k_lsd_extract, div_up(n, 256), 256, 0, src, n, first, (uint64_t*)ctx->jump.p, pe);
+        CK(cudaMemcpyAsync(ctx->h_seg_total + 7, counters + 8, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        if (ctx->debug_stop)
+        {
+          CK(cudaStreamSynchronize(ctx->stream));
+          ctx->last_geom = g;
+          ctx->err = "stopped behind phase 1 (debug_stop)";
+          return SZ4_ERR_ARG;
+        }
       }
-      PHASE(1);
-      if (g.shift == 0)
-        LAUNCH(ctx, k_chain, div_up(count, 256), 256, 0, (const uint64_t*)src, count, pe, g);
       else
       {
-        // with a dictionary the ring is read one slot off (DESIGN.md Q-dict): previousHash as a flat array, then the walk
+        uint64_t* bufA = (uint64_t*)ctx->scratch.p;
+        uint64_t* bufB = bufA + (((size_t)N + kPad + 1) & ~(size_t)1);
+        const uint32_t tiles = div_up(count, kSortTile);
+        const uint32_t hist_n = tiles * kSortBins;
+        RSV(hist, (size_t)hist_n * 4 + 64);
+        RSV(hist_scanned, (size_t)hist_n * 4 + 64);
+        uint32_t* hist = (uint32_t*)ctx->hist.p;
+        uint32_t* hscan = (uint32_t*)ctx->hist_scanned.p;
+        const uint32_t shifts[3] = { 0, 7, 14 }, masks[3] = { 127, 127, 63 };
+        uint64_t* src = nullptr;
+        uint64_t* dst = bufA;
+        for (int pass = 0; pass < 3; pass++)
+        {
+          if (pass == 0)
+            LAUNCH(ctx, k_sort_hist<true>, tiles, kSortThreads, 0, (const uint64_t*)nullptr, (const uint8_t*)data, first, count, shifts[0], masks[0], hist, tiles);
+          else
+            LAUNCH(ctx, k_sort_hist<false>, tiles, kSortThreads, 0, (const uint64_t*)src, (const uint8_t*)data, first, count, shifts[pass], masks[pass], hist, tiles);
+          int r = device_scan(ctx, hist, hscan, hist_n);
+          if (r != SZ4_OK) return r;
+          if (pass == 0)
+            LAUNCH(ctx, k_sort_scatter<true>, tiles, kSortThreads, 0, (const uint64_t*)nullptr, dst, (const uint8_t*)data, first, count, shifts[0], masks[0], (const uint32_t*)hscan, tiles);
+          else
+            LAUNCH(ctx, k_sort_scatter<false>, tiles, kSortThreads, 0, (const uint64_t*)src, dst, (const uint8_t*)data, first, count, shifts[pass], masks[pass], (const uint32_t*)hscan, tiles);
+          src = dst;
+          dst = (dst == bufA) ? bufB : bufA;
+        }
+        PHASE(1);
+        // the ring is read one slot off (DESIGN.md Q-dict): previousHash as a flat array, then the reference's walk
         LAUNCH(ctx, k_link, div_up(count, 256), 256, 0, (const uint64_t*)src, count, ph, g);
         LAUNCH(ctx, k_twice_save, div_up(g.n_blocks, 64), 64, 0, ph, saved_ph, g);
         LAUNCH(ctx, k_exact_walk, div_up(count, 256), 256, 0, (const uint8_t*)data, (const uint16_t*)ph, (const uint32_t*)saved_ph, pe, first, count, g);
+        LAUNCH(ctx, k_twice_save, div_up(g.n_blocks, 64), 64, 0, pe, saved_pe, g);
       }
-      LAUNCH(ctx, k_twice_save, div_up(g.n_blocks, 64), 64, 0, pe, saved_pe, g);
 
-      PHASE(2);
       // ---- helpers for runs of one byte (sz4_runs.cuh): only the undisturbed ring (no dictionary) uses them
       RSV(run_fwd, ((size_t)N + 64) * 4);
       RSV(ones_back, ((size_t)N + 64) * 2);
@@ -252,9 +304,11 @@ static int run_batch(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
       uint32_t* tile_order = tile_cost + n_tiles;
       LAUNCH(ctx, k_tile_cost, n_tiles, 256, 0, (const uint16_t*)pe, tiles_per_block, g, tile_cost);
       LAUNCH(ctx, k_tile_order, 1, 256, 0, (const uint32_t*)tile_cost, n_tiles, tile_order);
+      PHASE(2);
       LAUNCH(ctx, k_search, n_tiles, kSearchThreads, kSearchSmem, (const uint8_t*)data, (const uint16_t*)pe,
              (const uint32_t*)saved_pe, (const uint32_t*)ctx->run_fwd.p, (const uint16_t*)ctx->ones_back.p, mlen, mdist,
-             tiles_per_block, g, ctx->stage_bulk, ctx->fast_hops, ctx->fast_lanes, ctx->dense_a, ctx->dense_b, (const uint32_t*)tile_order);
+             tiles_per_block, g, ctx->stage_bulk, ctx->fast_hops, ctx->fast_lanes, ctx->dense_a, ctx->dense_b, (const uint32_t*)tile_order,
+             jump_tables ? (const uint16_t*)ctx->jump.p : (const uint16_t*)nullptr);
       PHASE(3);
       if (g.max_chain <= kLazyMax)
       {
@@ -265,9 +319,12 @@ static int run_batch(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
         GreedySeg* gsegs = (GreedySeg*)ctx->greedy_segs.p;
         uint32_t* gredo = (uint32_t*)(gsegs + n_segs);
         CK(cudaMemsetAsync(gredo, 0, 4, ctx->stream));
-        LAUNCH(ctx, k_greedy_spec, div_up(n_segs, 4), 128, 0, (const uint16_t*)pe, (const uint32_t*)saved_pe, mlen, mdist, gsegs, segs_per_block, g);
-        LAUNCH(ctx, k_greedy_join, div_up(g.n_blocks, 4), 128, 0, (const uint16_t*)pe, (const uint32_t*)saved_pe, mlen, mdist, gsegs, segs_per_block, gredo, g);
-        LAUNCH(ctx, k_greedy_apply, div_up(n_segs, 4), 128, 0, (const uint16_t*)pe, (const uint32_t*)saved_pe, mlen, mdist, (const GreedySeg*)gsegs, segs_per_block, g);
+        // (with the jump tables there is no array of the reference's own previousExact values: a position was searched
+        // iff it has an exact predecessor, iff k_search wrote a length)
+        const uint16_t* own_pe = jump_tables ? (const uint16_t*)nullptr : (const uint16_t*)pe;
+        LAUNCH(ctx, k_greedy_spec, div_up(n_segs, 4), 128, 0, own_pe, (const uint32_t*)saved_pe, mlen, mdist, gsegs, segs_per_block, g);
+        LAUNCH(ctx, k_greedy_join, div_up(g.n_blocks, 4), 128, 0, own_pe, (const uint32_t*)saved_pe, mlen, mdist, gsegs, segs_per_block, gredo, g);
+        LAUNCH(ctx, k_greedy_apply, div_up(n_segs, 4), 128, 0, own_pe, (const uint32_t*)saved_pe, mlen, mdist, (const GreedySeg*)gsegs, segs_per_block, g);
       }
       else
       {
@@ -283,6 +340,11 @@ static int run_batch(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
 
   if (ctx->debug_keep)
   {
+    RSV(dbg_pe, (size_t)N * 2 + 64);
+    if (g.shift == 0 && N >= g.first_ins + 4)
+      LAUNCH(ctx, k_debug_own4, div_up(N, 256), 256, 0, (const uint8_t*)data, (const uint16_t*)ctx->jump.p, (uint16_t*)ctx->dbg_pe.p, g);
+    else
+      CK(cudaMemcpyAsync(ctx->dbg_pe.p, pe, (size_t)N * 2, cudaMemcpyDeviceToDevice, ctx->stream));
     RSV(dbg_len, (size_t)N * 4 + 64);
     RSV(dbg_dist, (size_t)N * 2 + 64);
     CK(cudaMemcpyAsync(ctx->dbg_len.p, mlen, (size_t)N * 4, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -379,6 +441,7 @@ static int run_batch(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
   CK(cudaMemcpyAsync(ctx->h_seg_total + 1, ctx->dp_redo.p, 48, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaGetLastError());
+  if ((uint32_t)ctx->h_seg_total[7] != 0) { ctx->err = "k_lsd_pass: a tile waited for its predecessors in vain"; return SZ4_ERR_CUDA; }
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
   ctx->kernel_ms += ms;
@@ -596,7 +659,7 @@ void sz4_destroy(sz4_ctx* ctx)
 {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  DevBuf* all[] = { &ctx->greedy_segs, &ctx->dp_order, &ctx->tile_order, &ctx->data2, &ctx->seg2, &ctx->data, &ctx->ph, &ctx->pe, &ctx->mlen, &ctx->mdist, &ctx->scratch, &ctx->hist, &ctx->hist_scanned,
+  DevBuf* all[] = { &ctx->jump, &ctx->lsd_state, &ctx->lsd_misc, &ctx->dbg_pe, &ctx->greedy_segs, &ctx->dp_order, &ctx->tile_order, &ctx->data2, &ctx->seg2, &ctx->data, &ctx->ph, &ctx->pe, &ctx->mlen, &ctx->mdist, &ctx->scratch, &ctx->hist, &ctx->hist_scanned,
                     &ctx->partials, &ctx->seqs, &ctx->seq_count, &ctx->packed, &ctx->saved_ph, &ctx->saved_pe, &ctx->seeds,
                     &ctx->nseeds, &ctx->seg, &ctx->block_out, &ctx->seg_total, &ctx->dbg_len, &ctx->dbg_dist, &ctx->scalar_state,
                     &ctx->run_fwd, &ctx->ones_back, &ctx->flag_last, &ctx->flag_carry, &ctx->mfin, &ctx->dp_tasks,
@@ -630,6 +693,7 @@ int sz4_set_option(sz4_ctx* ctx, const char* name, long long value)
   if (!strcmp(name, "fast_lanes")) { if (value < 0 || value > 32) return SZ4_ERR_ARG; ctx->fast_lanes = (uint32_t)value; return SZ4_OK; }
   if (!strcmp(name, "profile")) { ctx->profile = value != 0; return SZ4_OK; }
   if (!strcmp(name, "force_scalar")) { ctx->force_scalar = value != 0; return SZ4_OK; }
+  if (!strcmp(name, "debug_stop")) { ctx->debug_stop = value != 0; return SZ4_OK; }
   ctx->err = "unknown option";
   return SZ4_ERR_ARG;
 }
@@ -795,8 +859,10 @@ int sz4_debug_fetch(sz4_ctx* ctx, const char* what, void* dst, size_t count)
   const Geom& g = ctx->last_geom;
   if (count > g.n_total) count = g.n_total;
   const void* src = nullptr; size_t elem = 0;
-  if (!strcmp(what, "pe")) { src = (uint16_t*)ctx->pe.p + kPad; elem = 2; }
+  if (!strcmp(what, "pe")) { src = ctx->dbg_pe.p; elem = 2; }
   else if (!strcmp(what, "ph")) { src = (uint16_t*)ctx->ph.p + kPad; elem = 2; }
+  else if (!strcmp(what, "pe8")) { src = (uint16_t*)ctx->pe.p + kPad; elem = 2; }
+  else if (!strcmp(what, "jump")) { src = ctx->jump.p; elem = 8; }
   else if (!strcmp(what, "len_found")) { src = ctx->dbg_len.p; elem = 4; }
   else if (!strcmp(what, "dist_found")) { src = ctx->dbg_dist.p; elem = 2; }
   else if (!strcmp(what, "len_final")) { src = ctx->dp_ran ? ctx->mfin.p : ctx->mlen.p; elem = 4; }

@@ -139,11 +139,12 @@ struct SearchView
 // runs (may be null) = run_fwd of sz4_runs.cuh: long stretches of one byte are stepped over by their lengths
 // instead of being compared word by word (same result; without it one position at the head of a run of a few
 // hundred KiB keeps its CTA busy for milliseconds).  Only valid where candidates share p's first bytes (no dictionary).
+// sure: the caller knows that the first len + 1 bytes are equal (a member of p's (len+1)-byte prefix class), phase 1 is skipped.
 __device__ __forceinline__ bool try_candidate(const SearchView& v, uint32_t p, uint32_t q, uint32_t stop, uint32_t& len, uint32_t& tail,
-                                              const uint32_t* runs)
+                                              const uint32_t* runs, bool sure = false)
 {
   const uint32_t need = len + 1;
-  if (len >= 4)
+  if (len >= 4 && !sure)
   {
     // phase 1, smallz4.h:224-233: bytes (0, need) in 4-byte groups from the top
     if (tail != v.word_at(q + len - 3)) return false;                  // first group from the top
@@ -187,13 +188,13 @@ __device__ __forceinline__ bool try_candidate(const SearchView& v, uint32_t p, u
 // Returns true when the walk is over; otherwise total/hop are left at the last member of the stretch.
 __device__ __forceinline__ bool walk_stretch(const SearchView& v, const uint32_t* run_fwd, const uint16_t* ones_back,
                                              uint32_t p, uint32_t stop, uint32_t R, uint32_t& total, uint32_t& hop,
-                                             uint32_t& len, uint32_t& dist, uint32_t& budget, uint32_t& tail)
+                                             uint32_t& len, uint32_t& dist, uint32_t& budget, uint32_t& tail, uint32_t limit)
 {
   const uint32_t len_in = len;
   const uint32_t C = stop - p;
   const uint32_t top = p - total;
   const uint32_t s = ones_back[top];
-  const uint32_t kmax = min(s, (uint32_t)kWindow - total);
+  const uint32_t kmax = min(s, limit - total);
   const uint32_t R0 = run_fwd[top];
   if (R0 > R)
   {
@@ -229,7 +230,7 @@ __device__ __forceinline__ bool walk_stretch(const SearchView& v, const uint32_t
       }
     }
   }
-  if (kmax < s) return true;                             // the next hop of 1 would exceed 65535 (smallz4.h:196)
+  if (kmax < s) return true;                             // the next hop of 1 would exceed 65535 (smallz4.h:196) or the chain's end
   if (len != len_in) tail = v.word_at(p + len - 3);
   total += s;
   hop = v.chain(p - total);
@@ -246,7 +247,7 @@ enum : uint32_t { kFastHops = SZ4_FAST_BLOCK };   // candidates per lane between
 
 // The rejecting path of the walk (smallz4.h:192-233) for up to `hops` candidates per lane; see k_search.
 __device__ __forceinline__ void fast_hops_loop(const SearchView& v, uint32_t hops, uint32_t& state, uint32_t& total, uint32_t& hop,
-                                               uint32_t run, uint32_t tail, smem_addr cbase, smem_addr dl, uint32_t min_lanes)
+                                               uint32_t run, uint32_t tail, smem_addr cbase, smem_addr dl, uint32_t min_lanes, uint32_t limit)
 {
   (void)v;
   uint32_t w0 = 0, w1 = 0;                                         // only looked at by lanes that loaded them
@@ -260,7 +261,7 @@ __device__ __forceinline__ void fast_hops_loop(const SearchView& v, uint32_t hop
     for (uint32_t un = 0; un < kFastHops; un++)
     {
       const uint32_t tot2 = total + hop;
-      const bool ends = hop == 0 || tot2 > kWindow;                // smallz4.h:192,196
+      const bool ends = hop == 0 || tot2 > limit;                  // smallz4.h:192,196 (limit: 65535, or where the chain ends)
       const bool walking = state == kWalk;
       const bool go = walking && !ends;
       // the candidate q = p - tot2: its chain entry (at 65535 its value ends the walk either way) and its bytes
@@ -356,6 +357,35 @@ k_tile_order(const uint32_t* cost, uint32_t n_tiles, uint32_t* order)
   }
 }
 
+// How far back the reference's chain of position p reaches (no dictionary).  The tables of sz4_lsd.cuh are "pure"
+// (previous position with the same prefix, at most 65535 back); the reference's chain is shorter in two cases:
+//  * legacy frames clear the tables at every block (smallz4.h:783-795): nothing in front of the block;
+//  * Q-twice: the position T twelve bytes in front of a block border is inserted again by the next block's
+//    lookback (smallz4.h:615-629), finds itself at distance 0 and zeroes its own entries.  Every chain that meets T
+//    ends there: the chains of the positions behind T whose four bytes hash like T's (smallz4.h:164,694-697).
+// word_p = the four bytes at p.
+__device__ __forceinline__ uint32_t chain_limit(const Geom& g, const uint8_t* data, uint32_t p, uint32_t word_p)
+{
+  if (g.legacy) return p >= g.halo ? min((uint32_t)kWindow, p - block_begin(g, (p - g.halo) / g.block_size)) : (uint32_t)kWindow;
+  if (p + kEndNoMatch - 1 < g.halo) return kWindow;
+  const uint32_t border = g.halo + (p + kEndNoMatch - 1 - g.halo) / g.block_size * g.block_size;   // the last one with T < p
+  if (border < kEndNoMatch) return kWindow;
+  const uint32_t T = border - kEndNoMatch;
+  if (p - T > kWindow || !is_twice_inserted(g, T)) return kWindow;
+  return hash20(ld32u(data + T)) == hash20(word_p) ? p - T : (uint32_t)kWindow;
+}
+
+// test hook (sz4_debug_fetch "pe"): previousExact as the reference's ring holds it, from the pure pe4 table
+__global__ void __launch_bounds__(256)
+k_debug_own4(const uint8_t* data, const uint16_t* jump16, uint16_t* out, Geom g)
+{
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= g.n_total) return;
+  const uint32_t d4 = jump16[(size_t)(p + 4) * 4];
+  const uint32_t lim = chain_limit(g, data, p, ld32u(data + p));
+  out[p] = (d4 != 0 && d4 <= lim && !is_twice_inserted(g, p)) ? (uint16_t)d4 : (uint16_t)0;
+}
+
 #ifdef SZ4_TILE_STATS
 // debugging aid (tools/tile_stats.py): duration and start of every tile in microseconds
 __device__ uint32_t g_tile_us[1 << 16], g_tile_t0[1 << 16];
@@ -365,7 +395,8 @@ __device__ __forceinline__ unsigned long long tile_clock() { unsigned long long 
 __global__ void __launch_bounds__(kSearchThreads, 1)
 k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, const uint32_t* run_fwd,
          const uint16_t* ones_back, uint32_t* mlen, uint16_t* mdist, uint32_t tiles_per_block, Geom g, int use_bulk,
-         uint32_t fast_hops, uint32_t fast_lanes, uint32_t dense_a, uint32_t dense_b, const uint32_t* tile_order)
+         uint32_t fast_hops, uint32_t fast_lanes, uint32_t dense_a, uint32_t dense_b, const uint32_t* tile_order,
+         const uint16_t* jump16)
 {
   SZ4_DYN_SMEM(smem);
   __shared__ uint64_t bar;
@@ -412,11 +443,15 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
   const uint32_t tw_own = tw_pos != 0xffffffffu ? saved_pe[(tw_pos + kEndNoMatch - g.halo) / g.block_size] : 0;
 
   const uint32_t lane = threadIdx.x & 31;
-  const uint32_t tlen = t1 - t0, n_pass = dense_a != 0 ? 3u : 1u;
+  // jump16 != nullptr: `pe` is pe8 and jump16 holds pe4..pe7 (sz4_lsd.cuh): keepers up to 8 bytes are jumped to, then
+  // the 8-byte chain is walked.  nullptr: the classic walk along previousExact (dictionary streams).
+  const bool jump = jump16 != nullptr;
+  const uint32_t tlen = t1 - t0, n_pass = (dense_a != 0 && !jump) ? 3u : 1u;
   const uint32_t* runs = g.shift == 0 ? run_fwd : nullptr;       // filled in only without a dictionary
   uint32_t state = kIdle;
   bool exhausted = false;
   uint32_t p = 0, len = 1, dist = 0, total = 0, hop = 0, budget = 0;
+  uint32_t limit = kWindow;            // the chain of p ends this far back (chain_limit)
   uint32_t run = 0;                    // bytes equal to data[p] from p on, when the stretch shortcut applies
   uint32_t tail = 0;                   // bytes p+len-3 .. p+len: the group a longer match has to reproduce first
   smem_addr cbase = v.s_pe, dl = v.s_data;   // &chain(p), &data[p + len - 3] in shared memory
@@ -435,7 +470,54 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
       const int leader = __ffs((int)idle) - 1;
       if (lane == (uint32_t)leader) base = atomicAdd(&next_pos, (uint32_t)__popc(idle));
       base = __shfl_sync(0xffffffffu, base, leader);
-      if (state == kIdle && !exhausted)
+      if (state == kIdle && !exhausted && jump)
+      {
+        const uint32_t idx = base + (uint32_t)__popc(idle & ((1u << lane) - 1));
+        p = t0 + idx;
+        if (idx >= tlen) exhausted = true;
+        else
+        {
+          // the reference searches p only if it has an exact predecessor its chain can reach (smallz4.h:712-717)
+          const uint32_t d4 = jump16[(size_t)(p + 4) * 4];
+          const uint32_t lim = d4 != 0 ? chain_limit(g, data, p, v.word_at(p)) : 0u;
+          if (d4 != 0 && d4 <= lim)
+          {
+            limit = lim; budget = g.max_chain; len = 1; tail = 0;
+            run = run_fwd[p]; if (run < 8) run = 0;                    // the 8-byte chain runs through p's run
+            cbase = v.s_pe + 2 * (p - v.clo);
+            // the first candidate is accepted unseen (smallz4.h:224-233 compare nothing while the best length is 1)
+            total = d4;
+            if (d4 == 1 && run != 0) { len = min(run, stop - p); tail = v.word_at(p + len - 3); }   // inside a run: the run's rest
+            else (void)try_candidate(v, p, p - total, stop, len, tail, runs);
+            dist = total;
+            bool finish = --budget == 0 || p + len + 1 > stop;
+            // keepers: the next candidate the reference keeps is the nearest one with the same len + 1 bytes
+            while (!finish && len < 8)
+            {
+              const uint32_t d = len == 7 ? v.chain(p) : jump16[(size_t)(p + len + 1) * 4 + (len - 3)];   // pe5..pe7, pe8
+              if (d == 0 || d > lim) { finish = true; break; }
+              total = d;
+              (void)try_candidate(v, p, p - total, stop, len, tail, runs, true);
+              dist = total;
+              finish = --budget == 0 || p + len + 1 > stop;
+            }
+            if (finish)
+            {
+              mlen[p] = len;
+              mdist[p] = (uint16_t)dist;
+            }
+            else
+            {
+              // at least eight bytes: the candidate is on p's 8-byte chain, which is walked from here
+              hop = v.chain(p - total);
+              dl = v.s_data + (p + len - 3 - v.dlo);
+              fast = p + len + 1 <= v.dhi || total + hop + v.dhi >= p + len + 1;
+              state = fast ? kWalk : kSlowWalk;
+            }
+          }
+        }
+      }
+      else if (state == kIdle && !exhausted)
       {
         // The tile is gone through three times: positions whose first two hops are short (a dense class: a long
         // chain) first, the bulk last -- so that the longest walks do not start when the tile is nearly done.
@@ -453,7 +535,7 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
           const uint32_t cls = n_pass == 1 ? 0u : (two < dense_a ? 0u : (two < dense_b ? 1u : 2u));
           if (own != 0 && cls == pass)
           {
-            state = kWalk; len = 1; dist = 0; total = 0; budget = g.max_chain; tail = 0;
+            state = kWalk; len = 1; dist = 0; total = 0; budget = g.max_chain; tail = 0; limit = kWindow;
             hop = first;
             run = 0;
             if (g.shift == 0) { run = run_fwd[p]; if (run < kMinMatch) run = 0; }
@@ -496,7 +578,7 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
     // ---- fast hops (smallz4.h:192-233, the rejecting path): follow the chain while the bytes a longer match
     // would need first differ.  A lane that meets anything else parks in a state for the slow part.
     // Written without branches around the loads: every lane executes the same 17 instructions per candidate.
-    fast_hops_loop(v, fast_hops, state, total, hop, run, tail, cbase, dl, fast_lanes);
+    fast_hops_loop(v, fast_hops, state, total, hop, run, tail, cbase, dl, fast_lanes, limit);
 
     // ---- slow part: candidates that passed the first byte, stretches, finished walks
     if (state >= kCheck)
@@ -507,7 +589,7 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
         // one hop of a lane whose match reaches beyond the staged bytes: every candidate gets the closer look,
         // and any 1-hop inside a run goes to the closed form
         const uint32_t tot2 = total + hop;
-        if (hop == 0 || tot2 > kWindow) state = kFinish;             // smallz4.h:192,196
+        if (hop == 0 || tot2 > limit) state = kFinish;               // smallz4.h:192,196
         else
         {
           total = tot2;
@@ -528,7 +610,7 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
         if (rejected) { }                                             // cannot be longer: on to the next candidate
         else if (state == kStretch || (run != 0 && hop == 1))
         {
-          finish = walk_stretch(v, run_fwd, ones_back, p, stop, run, total, hop, len, dist, budget, tail);
+          finish = walk_stretch(v, run_fwd, ones_back, p, stop, run, total, hop, len, dist, budget, tail, limit);
         }
         else if (try_candidate(v, p, p - total, stop, len, tail, runs))
         {
@@ -650,7 +732,7 @@ __device__ __forceinline__ GreedyBlock greedy_block(const uint32_t* saved_pe, co
   GreedyBlock k;
   k.b = block_begin(g, j); k.s_end = search_end(g, j);
   k.tw_pos = block_end(g, j) - kEndNoMatch;                      // the only position whose own entry is in saved_pe
-  k.tw = block_len(g, j) >= kEndNoMatch && is_twice_inserted(g, k.tw_pos);
+  k.tw = g.shift != 0 && block_len(g, j) >= kEndNoMatch && is_twice_inserted(g, k.tw_pos);   // (pure tables are never zeroed)
   k.tw_own = k.tw ? saved_pe[(k.tw_pos + kEndNoMatch - g.halo) / g.block_size] : 0;
   return k;
 }
@@ -681,7 +763,12 @@ __device__ __forceinline__ uint32_t greedy_walk(const GreedyBlock& k, const uint
     {
       const uint32_t q = cb + i * 32 + lane;
       n_own[i] = 0; n_len[i] = 0; n_dist[i] = 0;
-      if (q < s_end) { n_own[i] = (k.tw && q == k.tw_pos) ? k.tw_own : pe[q]; n_len[i] = mlen[q]; n_dist[i] = mdist[q]; }
+      if (q < s_end)
+      {
+        n_len[i] = mlen[q]; n_dist[i] = mdist[q];
+        // pe == nullptr (jump tables): searched iff the position has an exact predecessor iff k_search wrote a length
+        n_own[i] = pe == nullptr ? n_len[i] : ((k.tw && q == k.tw_pos) ? k.tw_own : pe[q]);
+      }
     }
   };
   auto commit = [&]()

@@ -234,5 +234,9 @@ static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigne
 static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return 0; }
 template <typename F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return 0; }
 
-#define SZ4_LAUNCH(kernel, grid, block, smem, stream, ...) \
-  emu::launch(dim3(grid), dim3(block), (size_t)(smem), [&]() { kernel(__VA_ARGS__); })
+// SZ4_EMU_TRACE=1 in the environment prints every launch (which kernel a crash belongs to)
+#define SZ4_LAUNCH(kernel, grid, block, smem, stream, ...)                                                        \
+  do {                                                                                                            \
+    if (getenv("SZ4_EMU_TRACE")) fprintf(stderr, "emu launch %s grid %u block %u\n", #kernel, (unsigned)dim3(grid).x, (unsigned)dim3(block).x); \
+    emu::launch(dim3(grid), dim3(block), (size_t)(smem), [&]() { kernel(__VA_ARGS__); });                         \
+  } while (0)
