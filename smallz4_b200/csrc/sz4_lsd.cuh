@@ -33,7 +33,28 @@ enum : uint32_t
   kLsdTile    = kLsdThreads * kLsdItems,   // 4096 elements per CTA
   kLsdBins    = 256,
   kLsdPasses  = 8,
+#ifndef SZ4_LSD_CHUNK
+#define SZ4_LSD_CHUNK (1u << 20)
+#endif
+  kLsdChunk   = SZ4_LSD_CHUNK,             // anchors a chunk owns (a multiple of the tile)
+  kLsdHalo    = 65536,                     // anchors in front of them that it sorts along: their possible predecessors
+  kLsdRegion  = kLsdChunk + kLsdHalo,      // elements per chunk in the buffers (a multiple of the tile)
+  kLsdTilesPerChunk = kLsdRegion / kLsdTile,
   kLsdSpin    = 1u << 24                   // polls of one look-back slot before the kernel gives up (never in practice)
+};
+
+// The sort is done chunk by chunk: chunk c owns the anchors [c*kLsdChunk, (c+1)*kLsdChunk) and sorts them together with
+// the kLsdHalo anchors in front (a predecessor is at most 65535 back), in its own region of the buffers.  The order
+// inside a chunk is all the tables need, and everything a chunk's extraction writes lies in a window of kLsdChunk
+// positions: the 2- and 8-byte scatters meet in L2 instead of each costing a DRAM sector.
+struct LsdGeom
+{
+  int32_t a0, a1;                          // anchors of the batch: [a0, a1)
+  uint32_t chunks;
+  __host__ __device__ __forceinline__ int32_t own_lo(uint32_t c) const { const int32_t x = (int32_t)(c * kLsdChunk); return x > a0 ? x : a0; }
+  __host__ __device__ __forceinline__ int32_t lo(uint32_t c) const { const int32_t x = (int32_t)(c * kLsdChunk) - (int32_t)kLsdHalo; return x > a0 ? x : a0; }
+  __host__ __device__ __forceinline__ int32_t hi(uint32_t c) const { const int64_t x = (int64_t)(c + 1) * kLsdChunk; return x < a1 ? (int32_t)x : a1; }
+  __host__ __device__ __forceinline__ uint32_t count(uint32_t c) const { return (uint32_t)(hi(c) - lo(c)); }
 };
 
 struct LsdBuf
@@ -55,19 +76,23 @@ __device__ __forceinline__ uint64_t lsd_key(const uint8_t* data, uint32_t a)
   return ((uint64_t)a0 << 32) | a1;
 }
 
-// ---- digit histograms: hist[v] = number of x in [lo, hi) with data[x] == v (the part all passes have in common).
-// Indices are signed: the first anchors look at the zero padding in front of the batch.
+// ---- digit histograms per chunk: hist[c][v] = number of x in [lo(c) - 1, hi(c) - 8) with data[x] == v (the part all
+// passes have in common).  Indices are signed: the first anchors look at the zero padding in front of the batch.
+// grid = chunks * kLsdHistSplit.
+enum : uint32_t { kLsdHistSplit = 8 };
 __global__ void __launch_bounds__(256)
-k_lsd_hist(const uint8_t* data, int32_t lo, int32_t hi, uint32_t* hist)
+k_lsd_hist(const uint8_t* data, LsdGeom lg, uint32_t* hist)
 {
   __shared__ uint32_t h[kLsdBins];
   h[threadIdx.x] = 0;
   __syncthreads();
+  const uint32_t c = blockIdx.x / kLsdHistSplit, part = blockIdx.x % kLsdHistSplit;
+  const int32_t lo = lg.lo(c) - 1, hi = max(lg.hi(c) - 8, lo);
   // 16 aligned bytes per thread and step; equal neighbours are counted in a register first (runs of one byte would
   // otherwise serialise on one counter)
   const int32_t lo16 = lo & ~15;
   const uint32_t steps = hi > lo16 ? (uint32_t)(hi - lo16 + 15) / 16 : 0;
-  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < steps; s += gridDim.x * blockDim.x)
+  for (uint32_t s = part * blockDim.x + threadIdx.x; s < steps; s += kLsdHistSplit * blockDim.x)
   {
     const int32_t x0 = lo16 + (int32_t)(s * 16);
     const uint4 q = *(const uint4*)(data + x0);
@@ -85,22 +110,25 @@ k_lsd_hist(const uint8_t* data, int32_t lo, int32_t hi, uint32_t* hist)
     if (cnt) atomicAdd(&h[last], cnt);
   }
   __syncthreads();
-  if (h[threadIdx.x]) atomicAdd(&hist[threadIdx.x], h[threadIdx.x]);
+  if (h[threadIdx.x]) atomicAdd(&hist[c * kLsdBins + threadIdx.x], h[threadIdx.x]);
 }
 
-// one CTA of 256 threads: bases[j-1][v] = number of anchors in [a0, a1) whose digit of pass j (data[a-j]) is below v.
-// common = histogram of data[clo, chi); pass j looks at data[a0-j, a1-j) = j-1 more bytes in front and 8-j behind.
+// one CTA of 256 threads per chunk: bases[c][j-1][v] = number of the chunk's anchors whose digit of pass j (data[a-j])
+// is below v.  Pass j looks at data[lo-j, hi-j) = the common part plus j-1 bytes in front and 8-j behind.
 __global__ void __launch_bounds__(256)
-k_lsd_bases(const uint8_t* data, int32_t a0, int32_t a1, int32_t clo, int32_t chi, const uint32_t* common, uint32_t* bases)
+k_lsd_bases(const uint8_t* data, LsdGeom lg, const uint32_t* common, uint32_t* bases)
 {
   __shared__ uint32_t ws[32], tot;
+  const uint32_t c = blockIdx.x;
+  const int32_t a0 = lg.lo(c), a1 = lg.hi(c);
+  const int32_t clo = a0 - 1, chi = max(a1 - 8, clo);
   for (int32_t j = 1; j <= (int32_t)kLsdPasses; j++)
   {
-    uint32_t c = common[threadIdx.x];
-    for (int32_t x = a0 - j; x < min(clo, a1 - j); x++) if (data[x] == threadIdx.x) c++;
-    for (int32_t x = max(chi, a0 - j); x < a1 - j; x++) if (data[x] == threadIdx.x) c++;
-    const uint32_t e = block_excl_scan(c, ws, &tot);
-    bases[(j - 1) * kLsdBins + threadIdx.x] = e;
+    uint32_t n = common[c * kLsdBins + threadIdx.x];
+    for (int32_t x = a0 - j; x < min(clo, a1 - j); x++) if (data[x] == threadIdx.x) n++;
+    for (int32_t x = max(chi, a0 - j); x < a1 - j; x++) if (data[x] == threadIdx.x) n++;
+    const uint32_t e = block_excl_scan(n, ws, &tot);
+    bases[(c * kLsdPasses + (j - 1)) * kLsdBins + threadIdx.x] = e;
   }
 }
 
@@ -130,9 +158,10 @@ __device__ __forceinline__ void lsd_post(uint64_t* p, uint64_t v)
 
 // kFirst: pass 1, elements are made from the data.  kCar: the input has a `car` array (passes 6..8).
 // level: 0, or the prefix length whose table is read off the input order (passes 5..8: 4..7).
+// grid = chunks * kLsdTilesPerChunk; element e of chunk c lives at c * kLsdRegion + e.
 template <bool kFirst, bool kCar>
-__global__ void __launch_bounds__(kLsdThreads)
-k_lsd_pass(LsdBuf in, LsdBuf out, const uint8_t* data, uint32_t a0, uint32_t n, uint32_t pass, uint32_t level, uint32_t first,
+__global__ void __launch_bounds__(kLsdThreads, 3)
+k_lsd_pass(LsdBuf in, LsdBuf out, const uint8_t* data, LsdGeom lg, uint32_t pass, uint32_t level, uint32_t first,
            const uint32_t* bases, uint64_t* tile_state, uint32_t* tile_counter, uint32_t* err)
 {
   __shared__ uint32_t cnt[kLsdThreads / 32][kLsdBins];
@@ -146,29 +175,41 @@ k_lsd_pass(LsdBuf in, LsdBuf out, const uint8_t* data, uint32_t a0, uint32_t n, 
   for (uint32_t k = threadIdx.x; k < (kLsdThreads / 32) * kLsdBins; k += kLsdThreads) (&cnt[0][0])[k] = 0;   // waits for running ones
   __syncthreads();
   const uint32_t tile = s_tile;
-  const uint32_t tile_base = tile * kLsdTile;
-  if (tile_base >= n) return;
+  const uint32_t chunk = tile / kLsdTilesPerChunk, ltile = tile % kLsdTilesPerChunk;
+  const uint32_t n = lg.count(chunk);                               // elements of this chunk
+  const uint32_t tile_base = ltile * kLsdTile;
+  if (tile_base >= n) return;                                       // (nobody looks back at an empty tile)
   const uint32_t tile_n = min((uint32_t)kLsdTile, n - tile_base);
   const uint32_t shift = (pass - 1) * 8;
+  const size_t region = (size_t)chunk * kLsdRegion;
+  const uint32_t a_lo = (uint32_t)lg.lo(chunk);
 
   // ---- load: warp w owns elements [w*512, (w+1)*512) of the tile, as 16 rows of 32 in order
   const uint32_t wbase = tile_base + warp * (32 * kLsdItems);
-  uint64_t key[kLsdItems], car[kLsdItems];
-  uint32_t pos[kLsdItems], rank[kLsdItems];
+  uint64_t key[kLsdItems];
+  uint32_t extra[kLsdItems];                                        // first the table entry read off the input order, then the rank
 #pragma unroll
   for (uint32_t r = 0; r < kLsdItems; r++)
   {
     const uint32_t i = wbase + r * 32 + lane;
-    const bool valid = i < n;
-    if (kFirst) { pos[r] = a0 + i; key[r] = valid ? lsd_key(data, a0 + i) : 0; }
-    else { pos[r] = valid ? in.pos[i] : 0; key[r] = valid ? in.key[i] : 0; }
-    car[r] = (kCar && valid) ? in.car[i] : 0;
+    if (kFirst) key[r] = i < n ? lsd_key(data, a_lo + i) : 0;
+    else key[r] = i < n ? in.key[region + i] : 0;
   }
   // ---- table of the input order: the left neighbour is the previous position with the same `level`-byte prefix
+  uint32_t pe[kLsdItems / 2];                                       // two 16-bit entries per register
+#pragma unroll
+  for (uint32_t r = 0; r < kLsdItems / 2; r++) pe[r] = 0;
   if (level != 0)
   {
+    uint32_t pos[kLsdItems];
+#pragma unroll
+    for (uint32_t r = 0; r < kLsdItems; r++)
+    {
+      const uint32_t i = wbase + r * 32 + lane;
+      pos[r] = i < n ? in.pos[region + i] : 0;
+    }
     uint64_t pk = 0; uint32_t pp = 0;                               // element in front of the warp's first one
-    if (wbase > 0 && wbase < n && lane == 0) { pk = in.key[wbase - 1]; pp = in.pos[wbase - 1]; }
+    if (wbase > 0 && wbase < n && lane == 0) { pk = in.key[region + wbase - 1]; pp = in.pos[region + wbase - 1]; }
     const uint32_t keep = 64 - 8 * level;
 #pragma unroll
     for (uint32_t r = 0; r < kLsdItems; r++)
@@ -180,7 +221,7 @@ k_lsd_pass(LsdBuf in, LsdBuf out, const uint8_t* data, uint32_t a0, uint32_t n, 
       const uint32_t d = pos[r] - lp;
       // both positions (anchor - level) must be ones the reference inserts (>= first)
       const bool hit = i < n && i > 0 && ((key[r] ^ lk) << keep) == 0 && d <= kWindow && lp >= first + level;
-      if (hit) car[r] |= (uint64_t)d << (16 * (level - 4));
+      if (hit) pe[r >> 1] |= d << (16 * (r & 1));
       pk = __shfl_sync(0xffffffffu, key[r], 31);
       pp = __shfl_sync(0xffffffffu, pos[r], 31);
     }
@@ -202,11 +243,11 @@ k_lsd_pass(LsdBuf in, LsdBuf out, const uint8_t* data, uint32_t a0, uint32_t n, 
       cnt[warp][digit] = start + (uint32_t)__popc(peers);
     }
     start = __shfl_sync(0xffffffffu, start, (int)leader);
-    rank[r] = start + before;
+    extra[r] = start + before;
     __syncwarp();
   }
   __syncthreads();
-  // ---- per digit (one thread each): rank of the warps, the tile's count, and the look-back over the tiles in front
+  // ---- per digit (one thread each): rank of the warps, the tile's count, and the look-back over the chunk's tiles in front
   {
     const uint32_t d = threadIdx.x;
     uint32_t run = 0;
@@ -220,11 +261,11 @@ k_lsd_pass(LsdBuf in, LsdBuf out, const uint8_t* data, uint32_t a0, uint32_t n, 
     lstart[d] = run;                                                // for now: this digit's count in the tile
     uint64_t* mine = tile_state + (size_t)tile * kLsdBins + d;
     uint32_t excl = 0;
-    if (tile == 0) lsd_post(mine, lsd_word(2, pass, run));
+    if (ltile == 0) lsd_post(mine, lsd_word(2, pass, run));
     else
     {
       lsd_post(mine, lsd_word(1, pass, run));
-      for (uint32_t t = tile; t-- > 0; )
+      for (uint32_t t = tile; t-- > tile - ltile; )
       {
         const uint64_t* there = tile_state + (size_t)t * kLsdBins + d;
         uint64_t s = lsd_peek(there);
@@ -239,7 +280,7 @@ k_lsd_pass(LsdBuf in, LsdBuf out, const uint8_t* data, uint32_t a0, uint32_t n, 
       }
       lsd_post(mine, lsd_word(2, pass, excl + run));
     }
-    gbase[d] = bases[(pass - 1) * kLsdBins + d] + excl;
+    gbase[d] = bases[(chunk * kLsdPasses + (pass - 1)) * kLsdBins + d] + excl;
   }
   __syncthreads();
   if (warp == 0)
@@ -254,19 +295,18 @@ k_lsd_pass(LsdBuf in, LsdBuf out, const uint8_t* data, uint32_t a0, uint32_t n, 
     for (uint32_t k = 0; k < kLsdBins / 32; k++) { lstart[lane * (kLsdBins / 32) + k] = run; run += c[k]; }
   }
   __syncthreads();
-  // ---- the tile in digit order in shared memory, then out with consecutive threads on consecutive addresses
-  uint32_t slot[kLsdItems];
+  // ---- the tile in digit order in shared memory, then out with consecutive threads on consecutive addresses;
+  // one array after the other through the same staging buffer (extra[] becomes the slot in the tile)
 #pragma unroll
   for (uint32_t r = 0; r < kLsdItems; r++)
   {
     const uint32_t i = wbase + r * 32 + lane;
-    slot[r] = 0xffffffffu;
     if (i < n)
     {
       const uint32_t digit = (uint32_t)(key[r] >> shift) & 255u;
-      slot[r] = lstart[digit] + cnt[warp][digit] + rank[r];
-      stage[slot[r]] = key[r];
-      sdig[slot[r]] = (uint8_t)digit;
+      extra[r] += lstart[digit] + cnt[warp][digit];
+      stage[extra[r]] = key[r];
+      sdig[extra[r]] = (uint8_t)digit;
     }
   }
   __syncthreads();
@@ -280,45 +320,62 @@ k_lsd_pass(LsdBuf in, LsdBuf out, const uint8_t* data, uint32_t a0, uint32_t n, 
     {
       const uint32_t digit = sdig[k];
       dst[m] = gbase[digit] + (k - lstart[digit]);
-      out.key[dst[m]] = stage[k];
+      out.key[region + dst[m]] = stage[k];
     }
   }
   __syncthreads();
   uint32_t* stage32 = (uint32_t*)stage;
 #pragma unroll
-  for (uint32_t r = 0; r < kLsdItems; r++) if (slot[r] != 0xffffffffu) stage32[slot[r]] = pos[r];
+  for (uint32_t r = 0; r < kLsdItems; r++)
+  {
+    const uint32_t i = wbase + r * 32 + lane;
+    if (i < n) stage32[extra[r]] = kFirst ? a_lo + i : in.pos[region + i];
+  }
   __syncthreads();
 #pragma unroll
-  for (uint32_t m = 0; m < kLsdItems; m++) if (dst[m] != 0xffffffffu) out.pos[dst[m]] = stage32[m * kLsdThreads + threadIdx.x];
+  for (uint32_t m = 0; m < kLsdItems; m++) if (dst[m] != 0xffffffffu) out.pos[region + dst[m]] = stage32[m * kLsdThreads + threadIdx.x];
   if (level != 0 || kCar)
   {
     __syncthreads();
 #pragma unroll
-    for (uint32_t r = 0; r < kLsdItems; r++) if (slot[r] != 0xffffffffu) stage[slot[r]] = car[r];
+    for (uint32_t r = 0; r < kLsdItems; r++)
+    {
+      const uint32_t i = wbase + r * 32 + lane;
+      if (i < n)
+      {
+        uint64_t v = kCar ? in.car[region + i] : 0;
+        if (level != 0) v |= (uint64_t)((pe[r >> 1] >> (16 * (r & 1))) & 0xffffu) << (16 * (level - 4));
+        stage[extra[r]] = v;
+      }
+    }
     __syncthreads();
 #pragma unroll
-    for (uint32_t m = 0; m < kLsdItems; m++) if (dst[m] != 0xffffffffu) out.car[dst[m]] = stage[m * kLsdThreads + threadIdx.x];
+    for (uint32_t m = 0; m < kLsdItems; m++) if (dst[m] != 0xffffffffu) out.car[region + dst[m]] = stage[m * kLsdThreads + threadIdx.x];
   }
 }
 
 // The final order (all eight bytes): pe8 from the left neighbour, and the tables out by position:
 //   jump[a] = { pe4[a-4], pe5[a-5], pe6[a-6], pe7[a-7] }  (8 bytes per anchor),  pe8[a-8]  (its own array: the match
-//   finder stages a 64 KiB window of it in shared memory).
+//   finder stages a 64 KiB window of it in shared memory).  A chunk writes the anchors it owns.
+// grid = chunks * kLsdRegion / 256.
 __global__ void __launch_bounds__(256)
-k_lsd_extract(LsdBuf in, uint32_t n, uint32_t first, uint64_t* jump, uint16_t* pe8)
+k_lsd_extract(LsdBuf in, LsdGeom lg, uint32_t first, uint64_t* jump, uint16_t* pe8)
 {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t chunk = blockIdx.x / (kLsdRegion / 256);
+  const uint32_t i = (blockIdx.x % (kLsdRegion / 256)) * 256 + threadIdx.x;
+  const uint32_t n = lg.count(chunk);
+  const size_t region = (size_t)chunk * kLsdRegion;
   const uint32_t lane = threadIdx.x & 31;
   const bool valid = i < n;
-  const uint64_t key = valid ? in.key[i] : 0;
-  const uint32_t pos = valid ? in.pos[i] : 0;
+  const uint64_t key = valid ? in.key[region + i] : 0;
+  const uint32_t pos = valid ? in.pos[region + i] : 0;
   uint64_t lk = __shfl_up_sync(0xffffffffu, key, 1);
   uint32_t lp = __shfl_up_sync(0xffffffffu, pos, 1);
-  if (lane == 0 && valid && i > 0) { lk = in.key[i - 1]; lp = in.pos[i - 1]; }
-  if (!valid) return;
+  if (lane == 0 && valid && i > 0) { lk = in.key[region + i - 1]; lp = in.pos[region + i - 1]; }
+  if (!valid || (int32_t)pos < lg.own_lo(chunk)) return;
   const uint32_t d = pos - lp;
   const bool hit = i > 0 && key == lk && d <= kWindow && lp >= first + 8;
-  jump[pos] = in.car[i];
+  jump[pos] = in.car[region + i];
   if (pos >= first + 8) pe8[pos - 8] = hit ? (uint16_t)d : (uint16_t)0;
 }
 

@@ -61,6 +61,7 @@ struct sz4_ctx
   uint32_t dense_a = 256, dense_b = 2048;   // k_search: first-two-hops distance below which a position goes in the first / second pass (0 = one pass)
   uint32_t fast_lanes = 8;     // ... which goes on in steps of eight while at least this many lanes are still walking
   // device memory (grow-only)
+  DevBuf tile_queue;                                     // k_start -> k_search: per tile, the positions whose walk goes on
   DevBuf jump, lsd_state, lsd_misc, dbg_pe;              // sz4_lsd.cuh: pe4..pe7 by anchor, look-back words, histograms / counters
   DevBuf greedy_segs;                                  // k_greedy_*: entry / leave of every segment, and the number of second walks
   DevBuf dp_order;                                     // k_dp_spec: its tasks in starting order
@@ -139,7 +140,10 @@ static int run_batch(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
   RSV(mdist, ((size_t)N + kPad) * 2);
   // the cost DP's four arrays; before that the ping-pong buffers of the sort (8-byte elements with a dictionary, else
   // key + position + carried tables = 20 bytes per anchor, twice)
-  const size_t lsd_n = (size_t)N + 5 - g.first_ins, lsd_stride = (lsd_n + 63) & ~(size_t)63;
+  LsdGeom lg;
+  lg.a0 = (int32_t)g.first_ins; lg.a1 = (int32_t)N + 5;             // anchors first .. N+4
+  lg.chunks = div_up((uint64_t)lg.a1, kLsdChunk);
+  const size_t lsd_stride = (size_t)lg.chunks * kLsdRegion;
   RSV(scratch, ((size_t)N + kPad) * 16 + 256 > 2 * 20 * lsd_stride ? ((size_t)N + kPad) * 16 + 256 : 2 * 20 * lsd_stride);
   RSV(saved_ph, (size_t)g.n_blocks * 4 + 64);
   RSV(saved_pe, (size_t)g.n_blocks * 4 + 64);
@@ -192,41 +196,39 @@ static int run_batch(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
     {
       if (jump_tables)
       {
-        const uint32_t n = (uint32_t)lsd_n;                           // anchors first .. N+4
-        const uint32_t tiles = div_up(n, kLsdTile);
+        const uint32_t tiles = lg.chunks * kLsdTilesPerChunk;
+        const size_t misc_words = (size_t)lg.chunks * kLsdBins + (size_t)lg.chunks * kLsdPasses * kLsdBins + 64;
         RSV(lsd_state, (size_t)tiles * kLsdBins * 8 + 64);
-        RSV(lsd_misc, (kLsdBins + kLsdPasses * kLsdBins + 64) * 4);
+        RSV(lsd_misc, misc_words * 4);
         RSV(jump, ((size_t)N + 64) * 8);
         uint32_t* common = (uint32_t*)ctx->lsd_misc.p;
-        uint32_t* bases = common + kLsdBins;
-        uint32_t* counters = bases + kLsdPasses * kLsdBins;           // [0..7] tile counters, [8] error flag
+        uint32_t* bases = common + (size_t)lg.chunks * kLsdBins;
+        uint32_t* counters = bases + (size_t)lg.chunks * kLsdPasses * kLsdBins;   // [0..7] tile counters, [8] error flag
         LsdBuf A, B;
         A.key = (uint64_t*)ctx->scratch.p; A.car = A.key + lsd_stride; A.pos = (uint32_t*)(A.car + lsd_stride);
         B.key = (uint64_t*)(A.pos + lsd_stride); B.car = B.key + lsd_stride; B.pos = (uint32_t*)(B.car + lsd_stride);
-        CK(cudaMemsetAsync(ctx->lsd_misc.p, 0, (kLsdBins + kLsdPasses * kLsdBins + 64) * 4, ctx->stream));
+        CK(cudaMemsetAsync(ctx->lsd_misc.p, 0, misc_words * 4, ctx->stream));
         CK(cudaMemsetAsync(ctx->lsd_state.p, 0, (size_t)tiles * kLsdBins * 8, ctx->stream));
-        const int32_t a0 = (int32_t)first, a1 = (int32_t)(first + n);
-        const int32_t clo = a0 - 1, chi = a1 - 8 > clo ? a1 - 8 : clo;
-        LAUNCH(ctx, k_lsd_hist, 148 * 8, 256, 0, (const uint8_t*)data, clo, chi, common);
-        LAUNCH(ctx, k_lsd_bases, 1, 256, 0, (const uint8_t*)data, a0, a1, clo, chi, (const uint32_t*)common, bases);
+        LAUNCH(ctx, k_lsd_hist, lg.chunks * kLsdHistSplit, 256, 0, (const uint8_t*)data, lg, common);
+        LAUNCH(ctx, k_lsd_bases, lg.chunks, 256, 0, (const uint8_t*)data, lg, (const uint32_t*)common, bases);
         LsdBuf src = A, dst = A;
         for (uint32_t pass = 1; pass <= kLsdPasses; pass++)
         {
           const uint32_t level = pass >= 5 ? pass - 1 : 0;             // passes 5..8 read pe4..pe7 off their input order
           if (pass == 1)
-            LAUNCH(ctx, (k_lsd_pass<true, false>), tiles, kLsdThreads, 0, src, dst, (const uint8_t*)data, first, n, pass, level, first,
+            LAUNCH(ctx, (k_lsd_pass<true, false>), tiles, kLsdThreads, 0, src, dst, (const uint8_t*)data, lg, pass, level, first,
                    (const uint32_t*)bases, (uint64_t*)ctx->lsd_state.p, counters + (pass - 1), counters + 8);
           else if (pass <= 5)
-            LAUNCH(ctx, (k_lsd_pass<false, false>), tiles, kLsdThreads, 0, src, dst, (const uint8_t*)data, first, n, pass, level, first,
+            LAUNCH(ctx, (k_lsd_pass<false, false>), tiles, kLsdThreads, 0, src, dst, (const uint8_t*)data, lg, pass, level, first,
                    (const uint32_t*)bases, (uint64_t*)ctx->lsd_state.p, counters + (pass - 1), counters + 8);
           else
-            LAUNCH(ctx, (k_lsd_pass<false, true>), tiles, kLsdThreads, 0, src, dst, (const uint8_t*)data, first, n, pass, level, first,
+            LAUNCH(ctx, (k_lsd_pass<false, true>), tiles, kLsdThreads, 0, src, dst, (const uint8_t*)data, lg, pass, level, first,
                    (const uint32_t*)bases, (uint64_t*)ctx->lsd_state.p, counters + (pass - 1), counters + 8);
           src = dst;
           dst = (dst.key == A.key) ? B : A;
         }
         PHASE(1);
-        LAUNCH(ctx, k_lsd_extract, div_up(n, 256), 256, 0, src, n, first, (uint64_t*)ctx->jump.p, pe);
+        LAUNCH(ctx, k_lsd_extract, lg.chunks * (kLsdRegion / 256), 256, 0, src, lg, first, (uint64_t*)ctx->jump.p, pe);
         CK(cudaMemcpyAsync(ctx->h_seg_total + 7, counters + 8, 4, cudaMemcpyDeviceToHost, ctx->stream));
         if (ctx->debug_stop)
         {
@@ -304,11 +306,23 @@ static int run_batch(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
       uint32_t* tile_order = tile_cost + n_tiles;
       LAUNCH(ctx, k_tile_cost, n_tiles, 256, 0, (const uint16_t*)pe, tiles_per_block, g, tile_cost);
       LAUNCH(ctx, k_tile_order, 1, 256, 0, (const uint32_t*)tile_cost, n_tiles, tile_order);
+      uint32_t* tile_count = nullptr;
+      uint32_t* tile_queue = nullptr;
+      if (jump_tables)
+      {
+        // the searches up to a match of eight bytes, one position per thread; the rest is queued per tile
+        RSV(tile_queue, ((size_t)n_tiles * kTile + n_tiles) * 4 + 64);
+        tile_queue = (uint32_t*)ctx->tile_queue.p;
+        tile_count = tile_queue + (size_t)n_tiles * kTile;
+        CK(cudaMemsetAsync(tile_count, 0, (size_t)n_tiles * 4, ctx->stream));
+        LAUNCH(ctx, k_start, div_up(N - g.halo, 256), 256, 0, (const uint8_t*)data, (const uint16_t*)ctx->jump.p, (const uint16_t*)pe,
+               (const uint32_t*)ctx->run_fwd.p, mlen, mdist, tile_count, tile_queue, tiles_per_block, g);
+      }
       PHASE(2);
       LAUNCH(ctx, k_search, n_tiles, kSearchThreads, kSearchSmem, (const uint8_t*)data, (const uint16_t*)pe,
              (const uint32_t*)saved_pe, (const uint32_t*)ctx->run_fwd.p, (const uint16_t*)ctx->ones_back.p, mlen, mdist,
              tiles_per_block, g, ctx->stage_bulk, ctx->fast_hops, ctx->fast_lanes, ctx->dense_a, ctx->dense_b, (const uint32_t*)tile_order,
-             jump_tables ? (const uint16_t*)ctx->jump.p : (const uint16_t*)nullptr);
+             (const uint32_t*)tile_count, (const uint32_t*)tile_queue);
       PHASE(3);
       if (g.max_chain <= kLazyMax)
       {
@@ -659,7 +673,7 @@ void sz4_destroy(sz4_ctx* ctx)
 {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  DevBuf* all[] = { &ctx->jump, &ctx->lsd_state, &ctx->lsd_misc, &ctx->dbg_pe, &ctx->greedy_segs, &ctx->dp_order, &ctx->tile_order, &ctx->data2, &ctx->seg2, &ctx->data, &ctx->ph, &ctx->pe, &ctx->mlen, &ctx->mdist, &ctx->scratch, &ctx->hist, &ctx->hist_scanned,
+  DevBuf* all[] = { &ctx->tile_queue, &ctx->jump, &ctx->lsd_state, &ctx->lsd_misc, &ctx->dbg_pe, &ctx->greedy_segs, &ctx->dp_order, &ctx->tile_order, &ctx->data2, &ctx->seg2, &ctx->data, &ctx->ph, &ctx->pe, &ctx->mlen, &ctx->mdist, &ctx->scratch, &ctx->hist, &ctx->hist_scanned,
                     &ctx->partials, &ctx->seqs, &ctx->seq_count, &ctx->packed, &ctx->saved_ph, &ctx->saved_pe, &ctx->seeds,
                     &ctx->nseeds, &ctx->seg, &ctx->block_out, &ctx->seg_total, &ctx->dbg_len, &ctx->dbg_dist, &ctx->scalar_state,
                     &ctx->run_fwd, &ctx->ones_back, &ctx->flag_last, &ctx->flag_carry, &ctx->mfin, &ctx->dp_tasks,

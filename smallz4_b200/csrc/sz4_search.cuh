@@ -140,7 +140,8 @@ struct SearchView
 // instead of being compared word by word (same result; without it one position at the head of a run of a few
 // hundred KiB keeps its CTA busy for milliseconds).  Only valid where candidates share p's first bytes (no dictionary).
 // sure: the caller knows that the first len + 1 bytes are equal (a member of p's (len+1)-byte prefix class), phase 1 is skipped.
-__device__ __forceinline__ bool try_candidate(const SearchView& v, uint32_t p, uint32_t q, uint32_t stop, uint32_t& len, uint32_t& tail,
+template <class View>
+__device__ __forceinline__ bool try_candidate(const View& v, uint32_t p, uint32_t q, uint32_t stop, uint32_t& len, uint32_t& tail,
                                               const uint32_t* runs, bool sure = false)
 {
   const uint32_t need = len + 1;
@@ -154,12 +155,21 @@ __device__ __forceinline__ bool try_candidate(const SearchView& v, uint32_t p, u
     for (; off > 0 && off + 4 > known; off -= 4)
       if (v.word_at(p + off) != v.word_at(q + off)) return false;
   }
-  // phase 2, smallz4.h:236-243
+  // phase 2, smallz4.h:236-243: four bytes at a time, then the last one to three -- here: the first byte that differs,
+  // not beyond `stop`
   uint32_t f = need, uniform = 0;
-  while (p + f + 4 <= stop)
+  for (;;)
   {
+    const uint32_t left = stop - (p + f);                              // (need <= stop - p: the caller's check)
+    if (left == 0) break;
     const uint32_t w = v.word_at(p + f);
-    if (w != v.word_at(q + f)) break;
+    const uint32_t x = w ^ v.word_at(q + f);
+    if (x != 0 || left < 4)
+    {
+      const uint32_t same = x != 0 ? ((uint32_t)__ffs((int)x) - 1) >> 3 : 4u;
+      f += min(same, left);
+      break;
+    }
     f += 4;
     if (runs != nullptr && w == __funnelshift_r(w, w, 8) && ++uniform >= 16)
     {
@@ -170,7 +180,6 @@ __device__ __forceinline__ bool try_candidate(const SearchView& v, uint32_t p, u
       uniform = 0;
     }
   }
-  while (p + f < stop && v.byte_at(p + f) == v.byte_at(q + f)) f++;
   len = f;
   tail = v.word_at(p + f - 3);
   return true;
@@ -386,6 +395,76 @@ k_debug_own4(const uint8_t* data, const uint16_t* jump16, uint16_t* out, Geom g)
   out[p] = (d4 != 0 && d4 <= lim && !is_twice_inserted(g, p)) ? (uint16_t)d4 : (uint16_t)0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// k_start: the first part of every search, one position per thread (no dictionary).  It takes the candidates the
+// reference keeps while the match is shorter than 8 bytes -- the nearest position with the same 4 bytes, then the
+// nearest with the same len+1 bytes (sz4_lsd.cuh) -- straight from the tables.  Most searches end here.  The ones that
+// reach 8 bytes and could still grow go into their tile's queue for k_search, which walks the 8-byte chain; their
+// state travels in mlen / mdist: length | improvements << 24 | 1 << 31, distance of the last candidate.
+// ---------------------------------------------------------------------------------------------
+enum : uint32_t { kStartLenMask = 0x00ffffffu, kStartCountShift = 24, kStartPending = 0x80000000u };
+
+struct GlobalView
+{
+  const uint8_t* g_data;
+  __device__ __forceinline__ uint32_t word_at(uint32_t pos) const
+  {
+    const uint32_t* w = (const uint32_t*)(g_data + (pos & ~3u));      // (the batch starts on an aligned address)
+    return __funnelshift_r(w[0], w[1], (pos & 3) * 8);
+  }
+};
+
+__global__ void __launch_bounds__(256)
+k_start(const uint8_t* data, const uint16_t* jump16, const uint16_t* pe8, const uint32_t* run_fwd, uint32_t* mlen, uint16_t* mdist,
+        uint32_t* tile_count, uint32_t* tile_queue, uint32_t tiles_per_block, Geom g)
+{
+  const uint32_t p = g.halo + blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t lane = threadIdx.x & 31;
+  GlobalView v; v.g_data = data;
+  uint32_t tile = 0xffffffffu;                                       // the tile whose queue p goes into, if any
+  if (p < g.n_total)
+  {
+    const uint32_t j = (p - g.halo) / g.block_size;
+    const uint32_t b = block_begin(g, j);
+    const uint32_t stop = block_end(g, j) - kEndLiterals;             // smallz4.h:736 end - BlockEndLiterals
+    const uint32_t d4 = p < search_end(g, j) ? jump16[(size_t)(p + 4) * 4] : 0u;
+    // the reference searches p only if it has an exact predecessor its chain can reach (smallz4.h:712-717)
+    const uint32_t lim = d4 != 0 ? chain_limit(g, data, p, v.word_at(p)) : 0u;
+    if (d4 != 0 && d4 <= lim)
+    {
+      uint32_t budget = g.max_chain, len = 1, tail = 0, total = d4, kept = 1;
+      uint32_t run = run_fwd[p]; if (run < 8) run = 0;
+      // the first candidate is accepted unseen (smallz4.h:224-233 compare nothing while the best length is 1)
+      if (d4 == 1 && run != 0) len = min(run, stop - p);              // inside a run: the rest of the run
+      else (void)try_candidate(v, p, p - total, stop, len, tail, run_fwd);
+      bool finish = --budget == 0 || p + len + 1 > stop;
+      while (!finish && len < 8)
+      {
+        const uint32_t d = len == 7 ? pe8[p] : jump16[(size_t)(p + len + 1) * 4 + (len - 3)];   // pe5..pe7, pe8
+        if (d == 0 || d > lim) { finish = true; break; }
+        total = d;
+        (void)try_candidate(v, p, p - total, stop, len, tail, run_fwd, true);
+        kept++;
+        finish = --budget == 0 || p + len + 1 > stop;
+      }
+      mdist[p] = (uint16_t)total;
+      if (finish) mlen[p] = len;
+      else
+      {
+        mlen[p] = len | (kept << kStartCountShift) | kStartPending;
+        tile = j * tiles_per_block + (p - b) / kTile;
+      }
+    }
+  }
+  // append to the tile's queue (a warp's positions nearly always belong to one tile: one atomic per warp)
+  const uint32_t peers = __match_any_sync(0xffffffffu, tile);
+  const int leader = __ffs((int)peers) - 1;
+  uint32_t at = 0;
+  if (tile != 0xffffffffu && lane == (uint32_t)leader) at = atomicAdd(&tile_count[tile], (uint32_t)__popc(peers));
+  at = __shfl_sync(0xffffffffu, at, leader);
+  if (tile != 0xffffffffu) tile_queue[(size_t)tile * kTile + at + (uint32_t)__popc(peers & ((1u << lane) - 1))] = p;
+}
+
 #ifdef SZ4_TILE_STATS
 // debugging aid (tools/tile_stats.py): duration and start of every tile in microseconds
 __device__ uint32_t g_tile_us[1 << 16], g_tile_t0[1 << 16];
@@ -396,7 +475,7 @@ __global__ void __launch_bounds__(kSearchThreads, 1)
 k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, const uint32_t* run_fwd,
          const uint16_t* ones_back, uint32_t* mlen, uint16_t* mdist, uint32_t tiles_per_block, Geom g, int use_bulk,
          uint32_t fast_hops, uint32_t fast_lanes, uint32_t dense_a, uint32_t dense_b, const uint32_t* tile_order,
-         const uint16_t* jump16)
+         const uint32_t* tile_count, const uint32_t* tile_queue)
 {
   SZ4_DYN_SMEM(smem);
   __shared__ uint64_t bar;
@@ -411,6 +490,7 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
   const uint32_t t0 = block_begin(g, j) + t * kTile;
   const uint32_t s_end = search_end(g, j);
   if (t0 >= s_end) return;
+  if (tile_queue != nullptr && tile_count[tile] == 0) return;       // nothing left to walk in this tile
   const uint32_t t1 = min(t0 + kTile, s_end);
   const uint32_t stop = block_end(g, j) - kEndLiterals;               // smallz4.h:736 end - BlockEndLiterals
 
@@ -443,10 +523,12 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
   const uint32_t tw_own = tw_pos != 0xffffffffu ? saved_pe[(tw_pos + kEndNoMatch - g.halo) / g.block_size] : 0;
 
   const uint32_t lane = threadIdx.x & 31;
-  // jump16 != nullptr: `pe` is pe8 and jump16 holds pe4..pe7 (sz4_lsd.cuh): keepers up to 8 bytes are jumped to, then
-  // the 8-byte chain is walked.  nullptr: the classic walk along previousExact (dictionary streams).
-  const bool jump = jump16 != nullptr;
-  const uint32_t tlen = t1 - t0, n_pass = (dense_a != 0 && !jump) ? 3u : 1u;
+  // tile_queue != nullptr: k_start has done every search up to a match of 8 bytes; `pe` is pe8 (sz4_lsd.cuh) and the
+  // tile's queue lists the positions whose walk goes on along the 8-byte chain.  nullptr: the classic walk along
+  // previousExact from the first candidate on (dictionary streams).
+  const bool jump = tile_queue != nullptr;
+  const uint32_t tlen = jump ? tile_count[tile] : t1 - t0, n_pass = (dense_a != 0 && !jump) ? 3u : 1u;
+  const uint32_t* queue = jump ? tile_queue + (size_t)tile * kTile : nullptr;
   const uint32_t* runs = g.shift == 0 ? run_fwd : nullptr;       // filled in only without a dictionary
   uint32_t state = kIdle;
   bool exhausted = false;
@@ -473,48 +555,24 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
       if (state == kIdle && !exhausted && jump)
       {
         const uint32_t idx = base + (uint32_t)__popc(idle & ((1u << lane) - 1));
-        p = t0 + idx;
         if (idx >= tlen) exhausted = true;
         else
         {
-          // the reference searches p only if it has an exact predecessor its chain can reach (smallz4.h:712-717)
-          const uint32_t d4 = jump16[(size_t)(p + 4) * 4];
-          const uint32_t lim = d4 != 0 ? chain_limit(g, data, p, v.word_at(p)) : 0u;
-          if (d4 != 0 && d4 <= lim)
-          {
-            limit = lim; budget = g.max_chain; len = 1; tail = 0;
-            run = run_fwd[p]; if (run < 8) run = 0;                    // the 8-byte chain runs through p's run
-            cbase = v.s_pe + 2 * (p - v.clo);
-            // the first candidate is accepted unseen (smallz4.h:224-233 compare nothing while the best length is 1)
-            total = d4;
-            if (d4 == 1 && run != 0) { len = min(run, stop - p); tail = v.word_at(p + len - 3); }   // inside a run: the run's rest
-            else (void)try_candidate(v, p, p - total, stop, len, tail, runs);
-            dist = total;
-            bool finish = --budget == 0 || p + len + 1 > stop;
-            // keepers: the next candidate the reference keeps is the nearest one with the same len + 1 bytes
-            while (!finish && len < 8)
-            {
-              const uint32_t d = len == 7 ? v.chain(p) : jump16[(size_t)(p + len + 1) * 4 + (len - 3)];   // pe5..pe7, pe8
-              if (d == 0 || d > lim) { finish = true; break; }
-              total = d;
-              (void)try_candidate(v, p, p - total, stop, len, tail, runs, true);
-              dist = total;
-              finish = --budget == 0 || p + len + 1 > stop;
-            }
-            if (finish)
-            {
-              mlen[p] = len;
-              mdist[p] = (uint16_t)dist;
-            }
-            else
-            {
-              // at least eight bytes: the candidate is on p's 8-byte chain, which is walked from here
-              hop = v.chain(p - total);
-              dl = v.s_data + (p + len - 3 - v.dlo);
-              fast = p + len + 1 <= v.dhi || total + hop + v.dhi >= p + len + 1;
-              state = fast ? kWalk : kSlowWalk;
-            }
-          }
+          // a search k_start left with a match of at least eight bytes: its last candidate is on p's 8-byte chain,
+          // which is walked from there
+          p = queue[idx];
+          const uint32_t packed = mlen[p];
+          len = packed & kStartLenMask;
+          budget = g.max_chain - ((packed >> kStartCountShift) & 15u);
+          total = mdist[p]; dist = total;
+          limit = chain_limit(g, data, p, v.word_at(p));
+          run = run_fwd[p]; if (run < 8) run = 0;                      // the 8-byte chain runs through p's run
+          cbase = v.s_pe + 2 * (p - v.clo);
+          tail = v.word_at(p + len - 3);
+          hop = v.chain(p - total);
+          dl = v.s_data + (p + len - 3 - v.dlo);
+          fast = p + len + 1 <= v.dhi || total + hop + v.dhi >= p + len + 1;
+          state = fast ? kWalk : kSlowWalk;
         }
       }
       else if (state == kIdle && !exhausted)
