@@ -344,9 +344,9 @@ def run_ours(args, rank, world, local_rank, sharded):
             "metric": METRIC, "value": total * args.steps / dt / 1e9, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
             "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": workload_name(total_mb) + (f", cut into {world} contiguous ranges of whole blocks with 128 KiB halos"
-                                                              if world > 1 else ""),
-                       "level": 9, "block_bytes": BLOCK,
+            "config": {"workload": workload_name(total_mb), "level": 9, "block_bytes": BLOCK,
+                       "sharding": (f"{world} contiguous ranges of whole blocks, one per GPU, each with a 128 KiB halo in front; no collective "
+                                    f"on the data path" if world > 1 else "one GPU, whole stream"),
                        "l2": f"every batch ({min(args.batch_blocks * 4, total_mb)} MB of input, ~50 B of arrays per byte) is larger than "
                              f"L2 (126 MB); no flush needed",
                        "batch_blocks": args.batch_blocks},

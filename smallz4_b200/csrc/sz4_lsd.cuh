@@ -356,10 +356,11 @@ k_lsd_pass(LsdBuf in, LsdBuf out, const uint8_t* data, LsdGeom lg, uint32_t pass
 
 // The final order (all eight bytes): pe8 from the left neighbour, and the tables out by position:
 //   jump[a] = { pe4[a-4], pe5[a-5], pe6[a-6], pe7[a-7] }  (8 bytes per anchor),  pe8[a-8]  (its own array: the match
-//   finder stages a 64 KiB window of it in shared memory).  A chunk writes the anchors it owns.
+//   finder stages a 64 KiB window of it in shared memory), and rank[a-8] = the element's index in the sorted arrays.
+// A chunk writes the anchors it owns.
 // grid = chunks * kLsdRegion / 256.
 __global__ void __launch_bounds__(256)
-k_lsd_extract(LsdBuf in, LsdGeom lg, uint32_t first, uint64_t* jump, uint16_t* pe8)
+k_lsd_extract(LsdBuf in, LsdGeom lg, uint32_t first, uint64_t* jump, uint16_t* pe8, uint32_t* rank)
 {
   const uint32_t chunk = blockIdx.x / (kLsdRegion / 256);
   const uint32_t i = (blockIdx.x % (kLsdRegion / 256)) * 256 + threadIdx.x;
@@ -376,7 +377,11 @@ k_lsd_extract(LsdBuf in, LsdGeom lg, uint32_t first, uint64_t* jump, uint16_t* p
   const uint32_t d = pos - lp;
   const bool hit = i > 0 && key == lk && d <= kWindow && lp >= first + 8;
   jump[pos] = in.car[region + i];
-  if (pos >= first + 8) pe8[pos - 8] = hit ? (uint16_t)d : (uint16_t)0;
+  if (pos >= first + 8)
+  {
+    pe8[pos - 8] = hit ? (uint16_t)d : (uint16_t)0;
+    rank[pos - 8] = (uint32_t)(region + i);                         // where k_long finds the position's class
+  }
 }
 
 }  // namespace sz4

@@ -59,8 +59,10 @@ struct sz4_ctx
   int      debug_stop = 0;     // tests: 1 = stop behind phase 1 (the tables stay for sz4_debug_fetch)
   uint32_t fast_hops = 64;     // k_search: at most this many candidates per lane and round in the fast loop ...
   uint32_t dense_a = 256, dense_b = 2048;   // k_search: first-two-hops distance below which a position goes in the first / second pass (0 = one pass)
+  uint32_t long_age = 8;       // k_search: rounds after which a walk is handed to k_long (tests lower it)
   uint32_t fast_lanes = 8;     // ... which goes on in steps of eight while at least this many lanes are still walking
   // device memory (grow-only)
+  DevBuf rank, long_list;                                // sz4_lsd.cuh / k_long: index of every position in the sorted arrays, handed-over walks
   DevBuf tile_queue;                                     // k_start -> k_search: per tile, the positions whose walk goes on
   DevBuf jump, lsd_state, lsd_misc, dbg_pe;              // sz4_lsd.cuh: pe4..pe7 by anchor, look-back words, histograms / counters
   DevBuf greedy_segs;                                  // k_greedy_*: entry / leave of every segment, and the number of second walks
@@ -192,6 +194,7 @@ static int run_batch(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
     const uint32_t first = g.first_ins;
     const uint32_t count = N >= first + 4 ? N - 3 - first : 0;
     const bool jump_tables = g.shift == 0;
+    LsdBuf lsd_sorted; lsd_sorted.key = nullptr; lsd_sorted.pos = nullptr; lsd_sorted.car = nullptr;
     if (count > 0)
     {
       if (jump_tables)
@@ -201,6 +204,7 @@ static int run_batch(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
         RSV(lsd_state, (size_t)tiles * kLsdBins * 8 + 64);
         RSV(lsd_misc, misc_words * 4);
         RSV(jump, ((size_t)N + 64) * 8);
+        RSV(rank, ((size_t)N + 64) * 4);
         uint32_t* common = (uint32_t*)ctx->lsd_misc.p;
         uint32_t* bases = common + (size_t)lg.chunks * kLsdBins;
         uint32_t* counters = bases + (size_t)lg.chunks * kLsdPasses * kLsdBins;   // [0..7] tile counters, [8] error flag
@@ -227,8 +231,9 @@ static int run_batch(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
           src = dst;
           dst = (dst.key == A.key) ? B : A;
         }
+        lsd_sorted = src;
         PHASE(1);
-        LAUNCH(ctx, k_lsd_extract, lg.chunks * (kLsdRegion / 256), 256, 0, src, lg, first, (uint64_t*)ctx->jump.p, pe);
+        LAUNCH(ctx, k_lsd_extract, lg.chunks * (kLsdRegion / 256), 256, 0, src, lg, first, (uint64_t*)ctx->jump.p, pe, (uint32_t*)ctx->rank.p);
         CK(cudaMemcpyAsync(ctx->h_seg_total + 7, counters + 8, 4, cudaMemcpyDeviceToHost, ctx->stream));
         if (ctx->debug_stop)
         {
@@ -319,10 +324,26 @@ static int run_batch(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
                (const uint32_t*)ctx->run_fwd.p, mlen, mdist, tile_count, tile_queue, tiles_per_block, g);
       }
       PHASE(2);
+      // the few walks that go on for thousands of candidates leave k_search for k_long (one warp each, over the sorted
+      // arrays, which are still in `scratch`)
+      const uint32_t long_cap = jump_tables ? N / 64 + 1024 : 0;
+      LongWalk* long_list = nullptr;
+      uint32_t* long_count = nullptr;
+      if (jump_tables)
+      {
+        RSV(long_list, (size_t)long_cap * sizeof(LongWalk) + 128);
+        long_list = (LongWalk*)((uint8_t*)ctx->long_list.p + 64);
+        long_count = (uint32_t*)ctx->long_list.p;
+        CK(cudaMemsetAsync(long_count, 0, 4, ctx->stream));
+      }
       LAUNCH(ctx, k_search, n_tiles, kSearchThreads, kSearchSmem, (const uint8_t*)data, (const uint16_t*)pe,
              (const uint32_t*)saved_pe, (const uint32_t*)ctx->run_fwd.p, (const uint16_t*)ctx->ones_back.p, mlen, mdist,
              tiles_per_block, g, ctx->stage_bulk, ctx->fast_hops, ctx->fast_lanes, ctx->dense_a, ctx->dense_b, (const uint32_t*)tile_order,
-             (const uint32_t*)tile_count, (const uint32_t*)tile_queue);
+             (const uint32_t*)tile_count, (const uint32_t*)tile_queue, long_list, long_count, long_cap, ctx->long_age);
+      if (jump_tables)
+        LAUNCH(ctx, k_long, 148 * 8, 256, 0, (const uint8_t*)data, (const uint64_t*)lsd_sorted.key, (const uint32_t*)lsd_sorted.pos,
+               (const uint32_t*)ctx->rank.p, (const LongWalk*)long_list, (const uint32_t*)long_count, long_cap,
+               (const uint32_t*)ctx->run_fwd.p, mlen, mdist, (uint32_t)kLsdRegion, g);
       PHASE(3);
       if (g.max_chain <= kLazyMax)
       {
@@ -673,7 +694,7 @@ void sz4_destroy(sz4_ctx* ctx)
 {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  DevBuf* all[] = { &ctx->tile_queue, &ctx->jump, &ctx->lsd_state, &ctx->lsd_misc, &ctx->dbg_pe, &ctx->greedy_segs, &ctx->dp_order, &ctx->tile_order, &ctx->data2, &ctx->seg2, &ctx->data, &ctx->ph, &ctx->pe, &ctx->mlen, &ctx->mdist, &ctx->scratch, &ctx->hist, &ctx->hist_scanned,
+  DevBuf* all[] = { &ctx->rank, &ctx->long_list, &ctx->tile_queue, &ctx->jump, &ctx->lsd_state, &ctx->lsd_misc, &ctx->dbg_pe, &ctx->greedy_segs, &ctx->dp_order, &ctx->tile_order, &ctx->data2, &ctx->seg2, &ctx->data, &ctx->ph, &ctx->pe, &ctx->mlen, &ctx->mdist, &ctx->scratch, &ctx->hist, &ctx->hist_scanned,
                     &ctx->partials, &ctx->seqs, &ctx->seq_count, &ctx->packed, &ctx->saved_ph, &ctx->saved_pe, &ctx->seeds,
                     &ctx->nseeds, &ctx->seg, &ctx->block_out, &ctx->seg_total, &ctx->dbg_len, &ctx->dbg_dist, &ctx->scalar_state,
                     &ctx->run_fwd, &ctx->ones_back, &ctx->flag_last, &ctx->flag_carry, &ctx->mfin, &ctx->dp_tasks,
@@ -707,6 +728,7 @@ int sz4_set_option(sz4_ctx* ctx, const char* name, long long value)
   if (!strcmp(name, "fast_lanes")) { if (value < 0 || value > 32) return SZ4_ERR_ARG; ctx->fast_lanes = (uint32_t)value; return SZ4_OK; }
   if (!strcmp(name, "profile")) { ctx->profile = value != 0; return SZ4_OK; }
   if (!strcmp(name, "force_scalar")) { ctx->force_scalar = value != 0; return SZ4_OK; }
+  if (!strcmp(name, "long_age")) { if (value < 0 || value > 1000000) return SZ4_ERR_ARG; ctx->long_age = (uint32_t)value; return SZ4_OK; }
   if (!strcmp(name, "debug_stop")) { ctx->debug_stop = value != 0; return SZ4_OK; }
   ctx->err = "unknown option";
   return SZ4_ERR_ARG;

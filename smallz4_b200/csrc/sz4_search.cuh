@@ -366,6 +366,8 @@ k_tile_order(const uint32_t* cost, uint32_t n_tiles, uint32_t* order)
   }
 }
 
+struct LongWalk { uint32_t p, len, dist, total, budget; };     // a walk k_search hands to k_long: state behind its last candidate
+
 // How far back the reference's chain of position p reaches (no dictionary).  The tables of sz4_lsd.cuh are "pure"
 // (previous position with the same prefix, at most 65535 back); the reference's chain is shorter in two cases:
 //  * legacy frames clear the tables at every block (smallz4.h:783-795): nothing in front of the block;
@@ -475,7 +477,8 @@ __global__ void __launch_bounds__(kSearchThreads, 1)
 k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, const uint32_t* run_fwd,
          const uint16_t* ones_back, uint32_t* mlen, uint16_t* mdist, uint32_t tiles_per_block, Geom g, int use_bulk,
          uint32_t fast_hops, uint32_t fast_lanes, uint32_t dense_a, uint32_t dense_b, const uint32_t* tile_order,
-         const uint32_t* tile_count, const uint32_t* tile_queue)
+         const uint32_t* tile_count, const uint32_t* tile_queue, LongWalk* long_list, uint32_t* long_count, uint32_t long_cap,
+         uint32_t long_age)
 {
   SZ4_DYN_SMEM(smem);
   __shared__ uint64_t bar;
@@ -534,6 +537,7 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
   bool exhausted = false;
   uint32_t p = 0, len = 1, dist = 0, total = 0, hop = 0, budget = 0;
   uint32_t limit = kWindow;            // the chain of p ends this far back (chain_limit)
+  uint32_t age = 0;                    // rounds this walk has been going on
   uint32_t run = 0;                    // bytes equal to data[p] from p on, when the stretch shortcut applies
   uint32_t tail = 0;                   // bytes p+len-3 .. p+len: the group a longer match has to reproduce first
   smem_addr cbase = v.s_pe, dl = v.s_data;   // &chain(p), &data[p + len - 3] in shared memory
@@ -573,6 +577,7 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
           dl = v.s_data + (p + len - 3 - v.dlo);
           fast = p + len + 1 <= v.dhi || total + hop + v.dhi >= p + len + 1;
           state = fast ? kWalk : kSlowWalk;
+          age = 0;
         }
       }
       else if (state == kIdle && !exhausted)
@@ -697,12 +702,91 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
         state = kIdle;
       }
     }
+    // A walk that has been going on for many rounds is one of the few very long ones (an 8-byte class with thousands of
+    // members in the window): the tile would end with it, most lanes idle.  It is handed to k_long, which takes the
+    // class 32 members at a time from the sorted array.  (Walks inside byte runs stay: they advance by whole runs.)
+    if (long_list != nullptr && (state == kWalk || state == kSlowWalk) && run == 0 && ++age > long_age)
+    {
+      const uint32_t slot = atomicAdd(long_count, 1u);
+      if (slot < long_cap)
+      {
+        LongWalk w; w.p = p; w.len = len; w.dist = dist; w.total = total; w.budget = budget;
+        long_list[slot] = w;
+        state = kIdle;
+      }
+      else age = 0;                                                  // the list is full: keep walking here
+    }
     idle = __ballot_sync(0xffffffffu, state == kIdle && !exhausted);
   }
 #ifdef SZ4_TILE_STATS
   __syncthreads();
   if (threadIdx.x == 0 && tile < (1u << 16)) { g_tile_us[tile] = (uint32_t)((tile_clock() - tile_t0) / 1000); g_tile_t0[tile] = (uint32_t)(tile_t0 / 1000); }
 #endif
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_long: the rest of the few very long walks, one warp each.  The members of p's 8-byte class are the elements in
+// front of p in the sorted arrays of sz4_lsd.cuh (same key, positions ascending), so the chain p would follow hop by
+// hop is read 32 members at a time, coalesced; the filter (the four bytes a longer match has to reproduce first,
+// smallz4.h:224-225) runs on all 32 at once and only a candidate that passes it gets the closer look.  Same candidates
+// in the same order as the walk: same result.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_long(const uint8_t* data, const uint64_t* skey, const uint32_t* spos, const uint32_t* rank, const LongWalk* list,
+       const uint32_t* count, uint32_t cap, const uint32_t* run_fwd, uint32_t* mlen, uint16_t* mdist, uint32_t region_elems, Geom g)
+{
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
+  const uint32_t n = min(*count, cap);
+  GlobalView v; v.g_data = data;
+  for (uint32_t e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < n; e += nwarps)
+  {
+    const LongWalk w = list[e];
+    const uint32_t p = w.p, a = p + 8;
+    uint32_t len = w.len, dist = w.dist, budget = w.budget;
+    const uint32_t stop = block_end(g, (p - g.halo) / g.block_size) - kEndLiterals;
+    const uint32_t limit = chain_limit(g, data, p, v.word_at(p));
+    uint32_t tail = v.word_at(p + len - 3);
+    const uint32_t r = rank[p];
+    const uint64_t key_p = skey[r];
+    const uint32_t lo = r / region_elems * region_elems;             // the chunk's first element
+    // the candidates are at r-1, r-2, ...; skip the ones the walk has seen (up to w.total back)
+    uint32_t k = 0;
+    for (;;)
+    {
+      const bool in = r >= lo + 1 + k + lane;
+      const bool seen = in && skey[r - 1 - k - lane] == key_p && spos[r - 1 - k - lane] + w.total >= a;
+      const uint32_t m = __ballot_sync(0xffffffffu, seen);         // (true for the nearest members, then false)
+      if (m != 0xffffffffu) { k += (uint32_t)__ffs((int)~m) - 1; break; }
+      k += 32;
+    }
+    for (;;)
+    {
+      const bool in = r >= lo + 1 + k + lane;
+      const uint32_t idx = in ? r - 1 - k - lane : r;
+      const uint32_t a2 = spos[idx];
+      const bool valid = in && skey[idx] == key_p && a - a2 <= limit;          // a member of the chain (smallz4.h:192-197)
+      const bool pass = valid && v.word_at(a2 - 8 + len - 3) == tail;
+      const uint32_t inv = __ballot_sync(0xffffffffu, !valid);
+      uint32_t m = __ballot_sync(0xffffffffu, pass);
+      if (inv != 0) m &= (1u << (__ffs((int)inv) - 1)) - 1;                      // nothing behind the chain's end
+      if (m == 0)
+      {
+        if (inv != 0) break;
+        k += 32;
+        continue;
+      }
+      const int l = __ffs((int)m) - 1;
+      const uint32_t qa = __shfl_sync(0xffffffffu, a2, l);
+      if (try_candidate(v, p, qa - 8, stop, len, tail, run_fwd))
+      {
+        dist = a - qa;
+        if (--budget == 0 || p + len + 1 > stop) break;              // smallz4.h:250, 205
+      }
+      k += (uint32_t)l + 1;
+    }
+    if (lane == 0) { mlen[p] = len; mdist[p] = (uint16_t)dist; }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------

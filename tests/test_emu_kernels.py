@@ -80,3 +80,17 @@ def test_dictionary_with_long_runs_uses_the_scalar_finder(emu):
 def test_periodic_data_leaves_the_cost_ring(emu):
     """matches far longer than the DP's shared-memory ring (8192 positions) and many length classes"""
     check(emu, (b"abcdefg" * 20000)[:120_000], 9)
+
+
+@pytest.mark.parametrize("age", [0, 2])
+def test_long_walks_are_handed_to_k_long(age):
+    """k_search hands walks that go on for many rounds to k_long (one warp per walk over the sorted arrays); with the
+    threshold at 0 or 2 rounds nearly every walk takes that path.  Several chunks of the sort, block borders included."""
+    c = emu_compressor(block_size=BS, batch_blocks=2, long_age=age)
+    try:
+        for kind, n, level in [("mixed", 3 * BS + 777, 9), ("binary", 200_000, 9), ("text", 150_000, 7), ("binary", 150_000, 4)]:
+            check(c, corpus.make(kind, n, 13).tobytes(), level)
+        check(c, (b"abcdefg" * 40000)[:250_000], 9)
+        check(c, (b"abcdefgh12345678" * 20000)[:300_000], 8)
+    finally:
+        c.close()

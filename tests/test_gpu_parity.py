@@ -257,3 +257,19 @@ def test_cli_matches_reference_flags(tmp_path):
     subprocess.run([cli, "-f", "-D", str(tmp_path / "dict.bin"), str(src), str(out)], check=True)
     assert out.read_bytes() == oracle_compress(data, 9, dictionary=d)[0]
     assert subprocess.run([cli, str(src), str(out)], capture_output=True).returncode != 0   # exists, no -f
+
+
+@pytest.mark.parametrize("age", [0, 3])
+def test_long_walk_kernel_agrees(gpu, age):
+    """k_long (warp per walk over the sorted arrays) against the lanes' walk: any hand-over threshold gives the same frame."""
+    data = corpus.make("mixed", 24 << 20, seed=77).tobytes()
+    a = gpu.compress(data, level=9)
+    gpu.set_option("long_age", age)
+    try:
+        b = gpu.compress(data, level=9)
+        c7 = gpu.compress(data[: 6 << 20], level=7)
+    finally:
+        gpu.set_option("long_age", 8)
+    assert a == b
+    assert c7 == gpu.compress(data[: 6 << 20], level=7)
+    assert a[: 7] == bytes([0x04, 0x22, 0x4D, 0x18, 0x40, 0x70, 0xDF])

@@ -1,14 +1,15 @@
 #!/usr/bin/env python
 """Source lines of one kernel ranked by executed warp instructions (and stall samples), from an ncu report captured with
---import-source on:   python tools/ncu_hot_lines.py report.ncu-rep kernel_regex [top]"""
+--import-source on:   python tools/ncu_hot_lines.py report.ncu-rep kernel_regex [top] [launch_skip]"""
 import csv, subprocess, sys
 
 
 def main():
     rep, kern = sys.argv[1], sys.argv[2]
     top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", "-k", "regex:" + kern],
-                         capture_output=True, text=True).stdout
+    skip = sys.argv[4] if len(sys.argv) > 4 else "0"
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", "-k", "regex:" + kern,
+                          "--launch-skip", skip, "--launch-count", "1"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     cur_file, hdr = "", None
     lines = []
