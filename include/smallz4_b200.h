@@ -53,7 +53,10 @@ const char* sz4_version(void);
 /* tuning / test knobs: "batch_blocks" (blocks per device batch), "block_size" (tests only: a multiple
    of 65536, >= 131072; 0 = format default), "stage_bulk" (1 = cp.async.bulk staging, 0 = plain loads),
    "debug_keep" (keep intermediates of the last batch for sz4_debug_fetch), "profile" (per-phase CUDA-event
-   timing for sz4_last_phase_ms), "force_scalar" (tests: route a dictionary stream through the scalar finder);
+   timing for sz4_last_phase_ms), "force_scalar" (tests: route a dictionary stream through the scalar finder), "allow_scalar_dict" (a -D stream
+   that contains 60 000 or more equal bytes in a row is refused with SZ4_ERR_ARG unless this is 1: then one device
+   thread replays the reference's ring, exact but slow), "stream_blocks" (sz4_lz4: blocks per batch, bounds its pinned
+   host memory), "long_age" (match finder: rounds after which a walk moves to the warp-per-walk kernel);
    match-finder scheduling, results never depend on them: "fast_hops" (candidates per lane and round, 1..1024),
    "fast_lanes" (lanes that must still be walking for a round to go on, 0..32), "dense_a" / "dense_b" (positions
    whose first two chain hops add up to less than this go first / second; dense_a = 0: one pass) */

@@ -31,6 +31,7 @@ namespace
 const uint32_t kBlockModern = 4u << 20;     // smallz4.h:124
 const uint32_t kBlockLegacy = 8u << 20;     // smallz4.h:127
 const uint32_t kHaloBytes   = 131072;       // >= 65535 + 12, keeps block starts 16-byte aligned
+const uint32_t kDictRunLimit = 60000;       // -D: runs from here on can fire the reference's long-run shortcut (65 299) inside the window
 
 struct DevBuf
 {
@@ -56,6 +57,7 @@ struct sz4_ctx
   int      stage_bulk = 1;
   int      debug_keep = 0;
   int      force_scalar = 0;
+  int      allow_scalar_dict = 0;   // 1: a -D stream with a run > 60 000 bytes is replayed by one device thread (sz4_scalar.cuh)
   int      debug_stop = 0;     // tests: 1 = stop behind phase 1 (the tables stay for sz4_debug_fetch)
   uint32_t fast_hops = 64;     // k_search: at most this many candidates per lane and round in the fast loop ...
   uint32_t dense_a = 256, dense_b = 2048;   // k_search: first-two-hops distance below which a position goes in the first / second pass (0 = one pass)
@@ -72,13 +74,18 @@ struct sz4_ctx
   DevBuf data, ph, pe, mlen, mdist, scratch, hist, hist_scanned, partials, seqs, seq_count, packed,
          saved_ph, saved_pe, seeds, nseeds, seg, block_out, seg_total, dbg_len, dbg_dist, scalar_state,
          run_fwd, ones_back, flag_last, flag_carry, mfin, dp_tasks, dp_count, dp_states, dp_overlays, dp_redo, dp_reach, seqs_tmp, path_segs;
-  unsigned long long* h_seg_total = nullptr;    // pinned: [0] segment bytes, [1] DP segments priced twice
+  uint8_t* h_in[2] = { nullptr, nullptr };       // sz4_lz4: pinned halves for the stream coming in ...
+  uint8_t* h_out[2] = { nullptr, nullptr };      // ... and the records going out
+  size_t   h_in_bytes = 0, h_out_bytes = 0;
+  uint32_t stream_blocks = 32; // sz4_lz4: blocks per batch (bounds the pinned host memory: 2 x 2 x 128 MiB)
+  unsigned long long* h_seg_total = nullptr;    // pinned: [0] segment bytes, [1..6] DP counters, [7] sort error flag, [8] longest byte run (-D)
   unsigned long long dp_redos = 0, path_redos = 0;
   bool               dp_ran = false;
   // stats
   double             kernel_ms = 0;
   unsigned long long launches = 0;
   Geom               last_geom;
+  bool               last_scalar = false;
   bool               attr_set = false, dp_attr_set = false;
 
   int fail(const char* what, cudaError_t e)
@@ -131,7 +138,8 @@ static int device_scan(sz4_ctx* ctx, const uint32_t* in, uint32_t* out, uint32_t
 // One batch: ctx->data holds kPad zero bytes, g.n_total input bytes, zero padding.  Produces the
 // concatenated block records in ctx->seg and their total size in *ctx->h_seg_total (after a sync).
 // ---------------------------------------------------------------------------------------------
-static int run_batch(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
+// batch_submit enqueues everything on ctx->stream and returns; batch_finish waits for it and reads the sizes.
+static int batch_submit(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
 {
   const uint32_t N = g.n_total;
   uint8_t* data = (uint8_t*)ctx->data.p + kPad;
@@ -171,6 +179,7 @@ static int run_batch(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
   uint32_t* saved_pe = (uint32_t*)ctx->saved_pe.p;
 
   ctx->h_seg_total[7] = 0;                                         // error flag of the sort's look-back
+  ctx->h_seg_total[8] = 0;
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
   CK(cudaMemsetAsync(ctx->ph.p, 0, ((size_t)N + 2 * kPad) * 2, ctx->stream));
   CK(cudaMemsetAsync(ctx->pe.p, 0, ((size_t)N + 2 * kPad) * 2, ctx->stream));
@@ -279,10 +288,10 @@ static int run_batch(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
         LAUNCH(ctx, k_twice_save, div_up(g.n_blocks, 64), 64, 0, pe, saved_pe, g);
       }
 
-      // ---- helpers for runs of one byte (sz4_runs.cuh): only the undisturbed ring (no dictionary) uses them
+      // ---- helpers for runs of one byte (sz4_runs.cuh): only the undisturbed ring (no dictionary) uses them in the
+      // search; a dictionary stream only asks for its longest run (see compress_blocks)
       RSV(run_fwd, ((size_t)N + 64) * 4);
       RSV(ones_back, ((size_t)N + 64) * 2);
-      if (g.shift == 0)
       {
         const uint32_t fchunks = div_up(N, kFlagChunk);
         RSV(flag_last, (size_t)fchunks * 4 + 64);
@@ -293,6 +302,21 @@ static int run_batch(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
         LAUNCH(ctx, k_flag_reduce<FlagFwdRuns>, fchunks, kFlagThreads, 0, fr, fl);
         LAUNCH(ctx, k_flag_carry, 1, 32, 0, (const uint32_t*)fl, fc, fchunks);
         LAUNCH(ctx, (k_flag_apply<FlagFwdRuns, uint32_t, true>), fchunks, kFlagThreads, 0, fr, (const uint32_t*)fc, (uint32_t*)ctx->run_fwd.p, 0xffffffffu);
+      }
+      if (g.shift != 0)
+      {
+        uint32_t* longest = (uint32_t*)ctx->seg_total.p + 4;
+        CK(cudaMemsetAsync(longest, 0, 4, ctx->stream));
+        // (only what the reference inserts into its chains counts: the zero padding in front of a short dictionary,
+        // smallz4.h:557-563, is never looked at)
+        LAUNCH(ctx, k_max_u32, 148 * 4, 256, 0, (const uint32_t*)ctx->run_fwd.p + g.first_ins, N - g.first_ins, longest);
+        CK(cudaMemcpyAsync(ctx->h_seg_total + 8, longest, 4, cudaMemcpyDeviceToHost, ctx->stream));
+      }
+      if (g.shift == 0)
+      {
+        const uint32_t fchunks = div_up(N, kFlagChunk);
+        uint32_t* fl = (uint32_t*)ctx->flag_last.p;
+        uint32_t* fc = (uint32_t*)ctx->flag_carry.p;
         FlagOnesBack fo; fo.pe = pe; fo.n = N;
         LAUNCH(ctx, k_flag_reduce<FlagOnesBack>, fchunks, kFlagThreads, 0, fo, fl);
         LAUNCH(ctx, k_flag_carry, 1, 32, 0, (const uint32_t*)fl, fc, fchunks);
@@ -326,7 +350,7 @@ static int run_batch(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
       PHASE(2);
       // the few walks that go on for thousands of candidates leave k_search for k_long (one warp each, over the sorted
       // arrays, which are still in `scratch`)
-      const uint32_t long_cap = jump_tables ? N / 64 + 1024 : 0;
+      const uint32_t long_cap = jump_tables ? N / 16 + 1024 : 0;
       LongWalk* long_list = nullptr;
       uint32_t* long_count = nullptr;
       if (jump_tables)
@@ -474,9 +498,24 @@ static int run_batch(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
   CK(cudaMemcpyAsync(ctx->h_seg_total, ctx->seg_total.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaMemcpyAsync(ctx->h_seg_total + 1, ctx->dp_redo.p, 48, cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->last_geom = g;
+  ctx->last_scalar = scalar_finder;
+  return SZ4_OK;
+}
+
+static int batch_finish(sz4_ctx* ctx)
+{
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaGetLastError());
   if ((uint32_t)ctx->h_seg_total[7] != 0) { ctx->err = "k_lsd_pass: a tile waited for its predecessors in vain"; return SZ4_ERR_CUDA; }
+  if (ctx->last_geom.shift != 0 && !ctx->last_scalar && (uint32_t)ctx->h_seg_total[8] >= kDictRunLimit)
+  {
+    // smallz4.h:632-643 meets the ring a dictionary shifts by one slot (DESIGN.md Q-dict): the parallel match finder is
+    // not exact there, and the reference's own output for such a stream does not decode.  Opt in for the exact replay.
+    ctx->err = "dictionary stream with a run of 60 000 or more equal bytes: set option allow_scalar_dict=1 for the "
+               "single-thread replay of the reference's ring (slow), or compress without -D";
+    return SZ4_ERR_ARG;
+  }
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
   ctx->kernel_ms += ms;
@@ -489,8 +528,13 @@ static int run_batch(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
       CK(cudaEventElapsedTime(&pm, ctx->pev[k], ctx->pev[k + 1]));
       ctx->phase_ms[k] += pm;
     }
-  ctx->last_geom = g;
   return SZ4_OK;
+}
+
+static int run_batch(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
+{
+  int r = batch_submit(ctx, g, scalar_finder);
+  return r != SZ4_OK ? r : batch_finish(ctx);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -546,13 +590,12 @@ static int compress_blocks(sz4_ctx* ctx, const StreamJob& job, size_t* out_len)
     memcpy(prefix.data() + kWindow - keep, dict + dict_len - keep, keep);
     first_ins = dict_len >= 65536 ? 0 : (uint32_t)(kWindow - keep);
   }
+  // With a dictionary the parallel finder is exact only while the long-run shortcut (smallz4.h:632) cannot fire.  By
+  // default such a stream is refused (batch_finish looks at the longest run the device found); with the option
+  // allow_scalar_dict the host decides up front and one device thread replays the reference's ring literally.
   bool scalar = false;
-  if (with_dict)
-  {
-    // the parallel finder is exact for dictionary streams only while the long-run shortcut
-    // (smallz4.h:632) cannot fire; otherwise one thread replays the reference's ring literally
-    scalar = ctx->force_scalar || has_long_run(job.src, job.n, 65280) || has_long_run(prefix.data(), prefix.size(), 60000);
-  }
+  if (with_dict && (ctx->allow_scalar_dict || ctx->force_scalar))
+    scalar = ctx->force_scalar || has_long_run(job.src, job.n, kDictRunLimit) || has_long_run(prefix.data(), prefix.size(), kDictRunLimit);
 
   const uint64_t blocks_total = (job.n + bs - 1) / bs;
   uint32_t per_batch = ctx->batch_blocks ? ctx->batch_blocks : 64;
@@ -646,6 +689,119 @@ static int compress_blocks(sz4_ctx* ctx, const StreamJob& job, size_t* out_len)
 }
 
 // ---------------------------------------------------------------------------------------------
+// sz4_lz4 without a dictionary: the stream is pulled and pushed batch by batch with bounded memory, like the reference
+// (smallz4.h:574-585 pulls 64 KiB requests, :770-780 pushes every block as it is finished, :798-804 keeps 64 KiB of
+// history).  Two pinned halves each way: while the kernels of batch k run, the host pushes the records of batch k-1
+// through send_bytes and pulls batch k+1 through get_bytes; the copies ride on ctx->copy_stream.
+// ---------------------------------------------------------------------------------------------
+static int compress_stream(sz4_ctx* ctx, sz4_get_bytes get_bytes, sz4_send_bytes send_bytes, void* user, uint32_t max_chain, bool legacy)
+{
+  const uint32_t bs = ctx->block_size_override ? ctx->block_size_override : (legacy ? kBlockLegacy : kBlockModern);
+  if (bs % 65536 != 0 || bs < 131072) { ctx->err = "block_size must be a multiple of 65536 and >= 131072"; return SZ4_ERR_ARG; }
+  uint32_t per_batch = ctx->stream_blocks < ctx->batch_blocks ? ctx->stream_blocks : ctx->batch_blocks;
+  if (per_batch < 1) per_batch = 1;
+  const size_t B = (size_t)per_batch * bs;
+  const size_t in_bytes = kHaloBytes + B, out_bytes = B + B / 255 + (size_t)per_batch * 68 + 64;
+  if (ctx->h_in_bytes < in_bytes || ctx->h_out_bytes < out_bytes)
+  {
+    for (int k = 0; k < 2; k++)
+    {
+      if (ctx->h_in[k]) cudaFreeHost(ctx->h_in[k]);
+      if (ctx->h_out[k]) cudaFreeHost(ctx->h_out[k]);
+      ctx->h_in[k] = ctx->h_out[k] = nullptr;
+    }
+    ctx->h_in_bytes = ctx->h_out_bytes = 0;
+    for (int k = 0; k < 2; k++)
+      if (cudaMallocHost((void**)&ctx->h_in[k], in_bytes) != cudaSuccess || cudaMallocHost((void**)&ctx->h_out[k], out_bytes) != cudaSuccess)
+      { ctx->err = "cudaMallocHost failed"; return SZ4_ERR_NOMEM; }
+    ctx->h_in_bytes = in_bytes; ctx->h_out_bytes = out_bytes;
+  }
+  // pull one batch into the half `slot` (behind the room for its history); 64 KiB requests, 0 bytes = end of input
+  auto pull = [&](int slot) -> size_t
+  {
+    uint8_t* at = ctx->h_in[slot] + kHaloBytes;
+    size_t have = 0;
+    while (have < B)
+    {
+      const size_t want = B - have < 65536 ? B - have : 65536;
+      const size_t got = get_bytes(at + have, want, user);
+      if (got == 0) break;
+      have += got;
+    }
+    return have;
+  };
+
+  int slot = 0;
+  size_t n = pull(0), prev_n = 0;
+  bool out_pending = false;
+  int out_slot = 0;
+  size_t out_len = 0;
+  uint64_t batch = 0;
+  while (n > 0)
+  {
+    const size_t halo = (batch == 0 || legacy) ? 0 : kHaloBytes;          // (every batch but the last is B >= 128 KiB long)
+    Geom g;
+    memset(&g, 0, sizeof(g));
+    g.halo = (uint32_t)halo; g.n_total = (uint32_t)(halo + n); g.block_size = bs; g.n_blocks = (uint32_t)((n + bs - 1) / bs);
+    g.max_chain = max_chain; g.legacy = legacy ? 1 : 0; g.stream_first = batch == 0 ? 1 : 0;
+    // input of this batch -> ctx->data2 (its last reader, batch k-2, is long done)
+    RSV(data2, (size_t)g.n_total + 2 * kPad + 64);
+    uint8_t* d = (uint8_t*)ctx->data2.p;
+    CK(cudaMemsetAsync(d, 0, kPad, ctx->copy_stream));
+    CK(cudaMemsetAsync(d + kPad + g.n_total, 0, kPad + 64, ctx->copy_stream));
+    CK(cudaMemcpyAsync(d + kPad, ctx->h_in[slot] + kHaloBytes - halo, halo + n, cudaMemcpyHostToDevice, ctx->copy_stream));
+    CK(cudaEventRecord(ctx->ev_in, ctx->copy_stream));
+    // the batch in front: wait for its kernels, start its records on their way out
+    if (batch > 0)
+    {
+      int r = batch_finish(ctx);
+      if (r != SZ4_OK) { cudaStreamSynchronize(ctx->copy_stream); return r; }
+      out_len = (size_t)*ctx->h_seg_total;
+      if (out_len > ctx->h_out_bytes) { cudaStreamSynchronize(ctx->copy_stream); ctx->err = "internal: records larger than their bound"; return SZ4_ERR_DST_SMALL; }
+      out_slot = (int)((batch - 1) & 1);
+      CK(cudaMemcpyAsync(ctx->h_out[out_slot], ctx->seg.p, out_len, cudaMemcpyDeviceToHost, ctx->copy_stream));
+      CK(cudaEventRecord(ctx->ev_out[0], ctx->copy_stream));
+      out_pending = true;
+      std::swap(ctx->seg, ctx->seg2);                                 // this batch writes the other half
+    }
+    std::swap(ctx->data, ctx->data2);
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_in, 0));
+    int r = batch_submit(ctx, g, false);
+    if (r != SZ4_OK) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(ctx->stream); return r; }
+    // while the kernels run: push the previous records, pull the next batch
+    if (out_pending)
+    {
+      CK(cudaEventSynchronize(ctx->ev_out[0]));
+      send_bytes(ctx->h_out[out_slot], out_len, user);
+      out_pending = false;
+    }
+    prev_n = n;
+    const int next = slot ^ 1;
+    size_t next_n = 0;
+    if (n == B)
+    {
+      // history for the next batch: the last 128 KiB of this one, in front of where its bytes go
+      // (the H2D copy of this batch out of h_in[slot] only reads)
+      if (!legacy) memcpy(ctx->h_in[next], ctx->h_in[slot] + kHaloBytes + B - kHaloBytes, kHaloBytes);
+      next_n = pull(next);
+    }
+    slot = next; n = next_n; batch++;
+  }
+  (void)prev_n;
+  if (batch > 0)
+  {
+    int r = batch_finish(ctx);
+    if (r != SZ4_OK) return r;
+    out_len = (size_t)*ctx->h_seg_total;
+    if (out_len > ctx->h_out_bytes) { ctx->err = "internal: records larger than their bound"; return SZ4_ERR_DST_SMALL; }
+    CK(cudaMemcpyAsync(ctx->h_out[0], ctx->seg.p, out_len, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    CK(cudaStreamSynchronize(ctx->copy_stream));
+    send_bytes(ctx->h_out[0], out_len, user);
+  }
+  return SZ4_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------------------
 extern "C" {
@@ -678,7 +834,7 @@ int sz4_create(sz4_ctx** out, int device)
       cudaEventCreateWithFlags(&ctx->ev_out[0], cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->ev_out[1], cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->ev_user, cudaEventDisableTiming) != cudaSuccess ||
-      cudaMallocHost((void**)&ctx->h_seg_total, 64) != cudaSuccess)
+      cudaMallocHost((void**)&ctx->h_seg_total, 128) != cudaSuccess)
   {
     fprintf(stderr, "smallz4_b200: cannot initialise CUDA device %d\n", device);
     delete ctx;
@@ -702,6 +858,7 @@ void sz4_destroy(sz4_ctx* ctx)
                     &ctx->path_segs };
   for (DevBuf* b : all) if (b->p) cudaFree(b->p);
   if (ctx->h_seg_total) cudaFreeHost(ctx->h_seg_total);
+  for (int k = 0; k < 2; k++) { if (ctx->h_in[k]) cudaFreeHost(ctx->h_in[k]); if (ctx->h_out[k]) cudaFreeHost(ctx->h_out[k]); }
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   for (int k = 0; k < 8; k++) if (ctx->pev[k]) cudaEventDestroy(ctx->pev[k]);
@@ -719,6 +876,7 @@ int sz4_set_option(sz4_ctx* ctx, const char* name, long long value)
 {
   if (!ctx || !name) return SZ4_ERR_ARG;
   if (!strcmp(name, "batch_blocks")) { if (value < 1) return SZ4_ERR_ARG; ctx->batch_blocks = (uint32_t)value; return SZ4_OK; }
+  if (!strcmp(name, "stream_blocks")) { if (value < 1 || value > 256) return SZ4_ERR_ARG; ctx->stream_blocks = (uint32_t)value; return SZ4_OK; }
   if (!strcmp(name, "block_size")) { ctx->block_size_override = (uint32_t)value; return SZ4_OK; }
   if (!strcmp(name, "stage_bulk")) { ctx->stage_bulk = value != 0; return SZ4_OK; }
   if (!strcmp(name, "debug_keep")) { ctx->debug_keep = value != 0; return SZ4_OK; }
@@ -728,6 +886,7 @@ int sz4_set_option(sz4_ctx* ctx, const char* name, long long value)
   if (!strcmp(name, "fast_lanes")) { if (value < 0 || value > 32) return SZ4_ERR_ARG; ctx->fast_lanes = (uint32_t)value; return SZ4_OK; }
   if (!strcmp(name, "profile")) { ctx->profile = value != 0; return SZ4_OK; }
   if (!strcmp(name, "force_scalar")) { ctx->force_scalar = value != 0; return SZ4_OK; }
+  if (!strcmp(name, "allow_scalar_dict")) { ctx->allow_scalar_dict = value != 0; return SZ4_OK; }
   if (!strcmp(name, "long_age")) { if (value < 0 || value > 1000000) return SZ4_ERR_ARG; ctx->long_age = (uint32_t)value; return SZ4_OK; }
   if (!strcmp(name, "debug_stop")) { ctx->debug_stop = value != 0; return SZ4_OK; }
   ctx->err = "unknown option";
@@ -840,7 +999,47 @@ int sz4_lz4(sz4_ctx* ctx, sz4_get_bytes get_bytes, sz4_send_bytes send_bytes, un
             const unsigned char* dict, size_t dict_len, int legacy, void* user)
 {
   if (!ctx || !get_bytes || !send_bytes) return SZ4_ERR_ARG;
-  // pull the stream in 64 KiB requests like the reference (smallz4.h:577, BufferSize)
+  CK(cudaSetDevice(ctx->device));
+  if (dict == nullptr || dict_len == 0)
+  {
+    ctx->kernel_ms = 0; ctx->launches = 0; ctx->dp_redos = 0; ctx->path_redos = 0;
+    for (int k = 0; k < 7; k++) ctx->phase_ms[k] = 0;
+    unsigned char mark[8];
+    send_bytes(mark, sz4_frame_header(mark, legacy), user);                                  // smallz4.h:479-496
+    if (max_chain == 0)
+    {
+      // level -0 (smallz4.h:511,765-780): blocks are stored, nothing to compute; legacy frames cannot mark stored
+      // blocks and the reference then writes empty ones -- so do we
+      const size_t bs = ctx->block_size_override ? ctx->block_size_override : (legacy ? kBlockLegacy : kBlockModern);
+      std::vector<uint8_t> block(bs);
+      for (;;)
+      {
+        size_t have = 0;
+        while (have < bs)
+        {
+          const size_t got = get_bytes(block.data() + have, bs - have < 65536 ? bs - have : 65536, user);
+          if (got == 0) break;
+          have += got;
+        }
+        if (have == 0) break;
+        const uint32_t tagged = legacy ? 0u : ((uint32_t)have | 0x80000000u);
+        const unsigned char word[4] = { (unsigned char)tagged, (unsigned char)(tagged >> 8), (unsigned char)(tagged >> 16), (unsigned char)(tagged >> 24) };
+        send_bytes(word, 4, user);
+        if (!legacy) send_bytes(block.data(), have, user);
+        if (have < bs) break;
+      }
+    }
+    else
+    {
+      int r = compress_stream(ctx, get_bytes, send_bytes, user, max_chain, legacy != 0);
+      if (r != SZ4_OK) return r;
+    }
+    const size_t e = sz4_frame_end(mark, legacy);                                           // smallz4.h:809-813
+    if (e) send_bytes(mark, e, user);
+    return SZ4_OK;
+  }
+  // With a dictionary the whole stream is taken in first: whether the parallel match finder applies depends on
+  // every byte of it (DESIGN.md Q-dict), and the reference's own -D frames do not decode anyway.
   std::vector<uint8_t> in;
   const size_t kChunk = 64 * 1024;
   for (;;)
@@ -851,7 +1050,7 @@ int sz4_lz4(sz4_ctx* ctx, sz4_get_bytes get_bytes, sz4_send_bytes send_bytes, un
     in.resize(at + got);
     if (got == 0) break;
   }
-  size_t cap = sz4_compress_bound(in.size(), legacy) + (dict_len ? in.size() : 0);
+  size_t cap = sz4_compress_bound(in.size(), legacy) + in.size();
   std::vector<uint8_t> out(cap);
   size_t len = 0;
   int r = sz4_compress_host(ctx, in.data(), in.size(), out.data(), cap, &len, max_chain, dict, dict_len, legacy);

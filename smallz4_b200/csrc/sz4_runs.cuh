@@ -115,4 +115,17 @@ __global__ void __launch_bounds__(kFlagThreads) k_flag_apply(F f, const uint32_t
   }
 }
 
+// maximum of an array (grid-stride; one atomic per CTA)
+__global__ void __launch_bounds__(256) k_max_u32(const uint32_t* in, uint32_t n, uint32_t* out)
+{
+  __shared__ uint32_t best;
+  if (threadIdx.x == 0) best = 0;
+  __syncthreads();
+  uint32_t m = 0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = max(m, in[i]);
+  if (m) atomicMax(&best, m);
+  __syncthreads();
+  if (threadIdx.x == 0 && best) atomicMax(out, best);
+}
+
 }  // namespace sz4

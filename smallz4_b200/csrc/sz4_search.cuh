@@ -252,7 +252,7 @@ enum : uint32_t { kIdle = 0, kWalk = 1, kCheck = 2, kStretch = 3, kFinish = 4, k
 #ifndef SZ4_FAST_BLOCK
 #define SZ4_FAST_BLOCK 8
 #endif
-enum : uint32_t { kFastHops = SZ4_FAST_BLOCK };   // candidates per lane between two looks at how many lanes still walk
+enum : uint32_t { kFastHops = SZ4_FAST_BLOCK, kTailLanes = 12 };   // candidates per lane between two looks at how many lanes still walk
 
 // The rejecting path of the walk (smallz4.h:192-233) for up to `hops` candidates per lane; see k_search.
 __device__ __forceinline__ void fast_hops_loop(const SearchView& v, uint32_t hops, uint32_t& state, uint32_t& total, uint32_t& hop,
@@ -366,6 +366,7 @@ k_tile_order(const uint32_t* cost, uint32_t n_tiles, uint32_t* order)
   }
 }
 
+enum : uint32_t { kLongWide = 4 };
 struct LongWalk { uint32_t p, len, dist, total, budget; };     // a walk k_search hands to k_long: state behind its last candidate
 
 // How far back the reference's chain of position p reaches (no dictionary).  The tables of sz4_lsd.cuh are "pure"
@@ -705,7 +706,17 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
     // A walk that has been going on for many rounds is one of the few very long ones (an 8-byte class with thousands of
     // members in the window): the tile would end with it, most lanes idle.  It is handed to k_long, which takes the
     // class 32 members at a time from the sorted array.  (Walks inside byte runs stay: they advance by whole runs.)
-    if (long_list != nullptr && (state == kWalk || state == kSlowWalk) && run == 0 && ++age > long_age)
+    // The same goes for the walks that are left when the tile's queue is empty and the warp cannot fill a third of its
+    // lanes any more: every further round would cost the warp as much as a full one.
+    bool hand_over = false;
+    if (long_list != nullptr)
+    {
+      const bool movable = (state == kWalk || state == kSlowWalk) && run == 0;
+      const bool drained = __any_sync(0xffffffffu, exhausted);
+      const uint32_t walking = __ballot_sync(0xffffffffu, state != kIdle);
+      hand_over = movable && (++age > long_age || (drained && (uint32_t)__popc(walking) < kTailLanes));
+    }
+    if (hand_over)
     {
       const uint32_t slot = atomicAdd(long_count, 1u);
       if (slot < long_cap)
@@ -760,30 +771,44 @@ k_long(const uint8_t* data, const uint64_t* skey, const uint32_t* spos, const ui
       if (m != 0xffffffffu) { k += (uint32_t)__ffs((int)~m) - 1; break; }
       k += 32;
     }
-    for (;;)
+    // kLongWide x 32 candidates per step: their loads are in flight together (a step is two dependent trips to L2)
+    for (bool done = false; !done; )
     {
-      const bool in = r >= lo + 1 + k + lane;
-      const uint32_t idx = in ? r - 1 - k - lane : r;
-      const uint32_t a2 = spos[idx];
-      const bool valid = in && skey[idx] == key_p && a - a2 <= limit;          // a member of the chain (smallz4.h:192-197)
-      const bool pass = valid && v.word_at(a2 - 8 + len - 3) == tail;
-      const uint32_t inv = __ballot_sync(0xffffffffu, !valid);
-      uint32_t m = __ballot_sync(0xffffffffu, pass);
-      if (inv != 0) m &= (1u << (__ffs((int)inv) - 1)) - 1;                      // nothing behind the chain's end
-      if (m == 0)
+      uint32_t a2[kLongWide]; bool valid[kLongWide], pass[kLongWide];
+#pragma unroll
+      for (uint32_t u = 0; u < kLongWide; u++)
       {
-        if (inv != 0) break;
-        k += 32;
-        continue;
+        const uint32_t off = k + u * 32 + lane;
+        const bool in = r >= lo + 1 + off;
+        const uint32_t idx = in ? r - 1 - off : r;
+        a2[u] = spos[idx];
+        valid[u] = in && skey[idx] == key_p;
       }
-      const int l = __ffs((int)m) - 1;
-      const uint32_t qa = __shfl_sync(0xffffffffu, a2, l);
-      if (try_candidate(v, p, qa - 8, stop, len, tail, run_fwd))
+#pragma unroll
+      for (uint32_t u = 0; u < kLongWide; u++)
       {
-        dist = a - qa;
-        if (--budget == 0 || p + len + 1 > stop) break;              // smallz4.h:250, 205
+        valid[u] = valid[u] && a - a2[u] <= limit;                   // a member of the chain (smallz4.h:192-197)
+        pass[u] = valid[u] && v.word_at(a2[u] - 8 + len - 3) == tail;
       }
-      k += (uint32_t)l + 1;
+      uint32_t advance = kLongWide * 32;
+#pragma unroll
+      for (uint32_t u = 0; u < kLongWide; u++)
+      {
+        if (advance != kLongWide * 32 || done) continue;             // (uniform: an earlier group has decided)
+        const uint32_t inv = __ballot_sync(0xffffffffu, !valid[u]);
+        uint32_t m = __ballot_sync(0xffffffffu, pass[u]);
+        if (inv != 0) m &= (1u << (__ffs((int)inv) - 1)) - 1;        // nothing behind the chain's end
+        if (m == 0) { if (inv != 0) done = true; continue; }
+        const int l = __ffs((int)m) - 1;
+        const uint32_t qa = __shfl_sync(0xffffffffu, a2[u], l);
+        if (try_candidate(v, p, qa - 8, stop, len, tail, run_fwd))
+        {
+          dist = a - qa;
+          if (--budget == 0 || p + len + 1 > stop) done = true;      // smallz4.h:250, 205
+        }
+        advance = u * 32 + (uint32_t)l + 1;                          // go on behind that candidate (with the new length)
+      }
+      k += advance;
     }
     if (lane == 0) { mlen[p] = len; mdist[p] = (uint16_t)dist; }
   }

@@ -72,9 +72,19 @@ def test_dictionary_ring_shift(emu, dict_len):
         check(emu, data, level, dictionary=d)
 
 
-def test_dictionary_with_long_runs_uses_the_scalar_finder(emu):
-    check(emu, bytes(150_000), 9, dictionary=bytes(65536))
-    check(emu, bytes(150_000), 3, dictionary=bytes(30000))
+def test_dictionary_with_long_runs_is_fenced(emu):
+    """-D plus a run long enough for the reference's long-run shortcut: refused by default (the device finds the run),
+    replayed exactly by one device thread with allow_scalar_dict=1."""
+    from smallz4_b200.api import Sz4Error
+    with pytest.raises(Sz4Error, match="allow_scalar_dict"):
+        emu.compress(bytes(150_000), level=9, dictionary=bytes(65536))
+    emu.set_option("allow_scalar_dict", 1)
+    try:
+        check(emu, bytes(150_000), 9, dictionary=bytes(65536))
+        check(emu, bytes(150_000), 3, dictionary=bytes(30000))
+    finally:
+        emu.set_option("allow_scalar_dict", 0)
+    check(emu, corpus.make("text", 30_000, 5).tobytes(), 9, dictionary=bytes(1000))     # a short run of zeros is fine
 
 
 def test_periodic_data_leaves_the_cost_ring(emu):
@@ -92,5 +102,27 @@ def test_long_walks_are_handed_to_k_long(age):
             check(c, corpus.make(kind, n, 13).tobytes(), level)
         check(c, (b"abcdefg" * 40000)[:250_000], 9)
         check(c, (b"abcdefgh12345678" * 20000)[:300_000], 8)
+    finally:
+        c.close()
+
+
+@pytest.mark.parametrize("n,level,legacy", [(0, 9, False), (5, 9, False), (2 * BS, 9, False), (2 * BS + 1, 3, False),
+                                            (5 * BS + 777, 9, False), (3 * BS + 5, 5, True), (300_000, 0, False), (300_000, 0, True)])
+def test_lz4_streams_batch_by_batch(n, level, legacy):
+    """sz4_lz4 pulls and pushes batch by batch (two blocks per batch here) with ragged get_bytes returns; same frame."""
+    c = emu_compressor(block_size=BS, batch_blocks=2, stream_blocks=2)
+    try:
+        data = corpus.make("mixed", n, 21).tobytes()
+        pos, out = [0], []
+
+        def get(k):
+            chunk = data[pos[0]: pos[0] + min(k, 50_000)]
+            pos[0] += len(chunk)
+            return chunk
+
+        c.lz4(get, out.append, max_chain_length=(65535 if level == 9 else level), use_legacy_format=legacy)
+        want, _ = oracle_compress(data, level, legacy, block_size=BS)
+        assert b"".join(out) == want
+        assert len(out) >= 2 + (n > 2 * BS)            # header, records batch by batch, end mark: not one big push
     finally:
         c.close()
