@@ -354,6 +354,293 @@ k_lsd_pass(LsdBuf in, LsdBuf out, const uint8_t* data, LsdGeom lg, uint32_t pass
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Passes 2..8, second form: persistent CTAs (one per SM) whose input tiles arrive by bulk-async copies
+// (cp.async.bulk -> UBLKCP, completion on an mbarrier) two tiles deep, so the loads of the next tile are in flight
+// while this one is ranked and written.  The tile is read where the copy put it: ranking gives every element its slot,
+// the inverse (slot -> element) is written to shared memory, and the output loop gathers from the staged input and
+// stores with consecutive threads on consecutive addresses.  The look-back reads four predecessors per trip.
+// ---------------------------------------------------------------------------------------------
+enum : uint32_t
+{
+  kLsd2Threads = 512,
+  kLsd2Items   = kLsdTile / kLsd2Threads,                              // 8
+  kLsd2Warps   = kLsd2Threads / 32,
+  kLsd2CntBytes = kLsd2Warps * kLsdBins * 4
+};
+// dynamic shared memory: kHalves input tiles (key, car, pos), slot -> element, per-warp digit counters, digit starts
+template <uint32_t kHalves, bool kWithCar, bool kWithPos> struct Lsd2Layout
+{
+  static constexpr uint32_t key = 0, car = key + kHalves * kLsdTile * 8, pos = car + (kWithCar ? kHalves * kLsdTile * 8 : 0),
+                            src = pos + (kWithPos ? kHalves * kLsdTile * 4 : 0), cnt = src + kLsdTile * 2, misc = cnt + kLsd2CntBytes,
+                            bytes = misc + 2 * kLsdBins * 4 + 64;
+};
+
+#ifndef SZ4_EMU
+__device__ __forceinline__ uint32_t lsd_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void lsd_bulk(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+  for (uint32_t o = 0; o < bytes; o += 16384)
+  {
+    const uint32_t piece = min(16384u, bytes - o);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(lsd_smem_u32((const unsigned char*)dst + o)), "l"((const unsigned char*)src + o), "r"(piece), "r"(lsd_smem_u32(bar)) : "memory");
+  }
+}
+#endif
+
+// kMode: 0 = pass 1 (elements are made from the data), 1 = passes 2..4 (key, pos), 2 = pass 5 (key, pos in; pe4 starts
+// `car`), 3 = passes 6..8 (key, pos, car).
+// kPersist: one CTA per SM runs through the tiles, two halves of shared memory, the next tile's copies in flight while
+// this one is processed.  Otherwise: one tile per CTA, one half, two CTAs per SM (registers: 64 x 512 x 2).
+template <uint32_t kMode, bool kPersist>
+__global__ void __launch_bounds__(kLsd2Threads, kPersist ? 1 : 2)
+k_lsd_pass2(LsdBuf in, LsdBuf out, const uint8_t* data, LsdGeom lg, uint32_t pass, uint32_t first, const uint32_t* bases,
+            uint64_t* tile_state, uint32_t* tile_counter, uint32_t total_tiles, uint32_t* err)
+{
+  constexpr bool kFirst = kMode == 0, kCar = kMode == 3, kCarOut = kMode >= 2;
+  const uint32_t level = kCarOut ? pass - 1 : 0;                     // the table read off the input order (passes 5..8: pe4..pe7)
+  SZ4_DYN_SMEM(smem);
+  __shared__ uint64_t bar[2];
+  __shared__ uint32_t s_next;
+  typedef Lsd2Layout<kPersist ? 2 : 1, kCarOut, !kFirst> L;
+  uint64_t* s_key = (uint64_t*)(smem + L::key);
+  uint64_t* s_car = (uint64_t*)(smem + L::car);
+  uint32_t* s_pos = (uint32_t*)(smem + L::pos);
+  uint16_t* s_src = (uint16_t*)(smem + L::src);
+  uint32_t (*cnt)[kLsdBins] = (uint32_t (*)[kLsdBins])(smem + L::cnt);
+  uint32_t* lstart = (uint32_t*)(smem + L::misc);
+  uint32_t* gbase = lstart + kLsdBins;
+
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t shift = (pass - 1) * 8;
+
+  // input of tile `t` -> half `b`.  Sizes are rounded up to 16 bytes (the region has room: it is a multiple of the tile).
+  auto fetch = [&](uint32_t t, uint32_t b)
+  {
+    const uint32_t chunk = t / kLsdTilesPerChunk, ltile = t % kLsdTilesPerChunk;
+    const uint32_t n = lg.count(chunk), tile_base = ltile * kLsdTile;
+    if (tile_base >= n) return;                                        // an empty tile: nothing to wait for either
+    if (kFirst) return;                                                // (pass 1 makes its elements itself)
+    const uint32_t tile_n = (min((uint32_t)kLsdTile, n - tile_base) + 3) & ~3u;
+    const size_t at = (size_t)chunk * kLsdRegion + tile_base;
+#ifndef SZ4_EMU
+    const uint32_t bytes = tile_n * (kCar ? 20u : 12u);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the half was read and written by plain accesses before
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(lsd_smem_u32(&bar[b])), "r"(bytes) : "memory");
+    lsd_bulk(s_key + b * kLsdTile, in.key + at, tile_n * 8, &bar[b]);
+    lsd_bulk(s_pos + b * kLsdTile, in.pos + at, tile_n * 4, &bar[b]);
+    if (kCar) lsd_bulk(s_car + b * kLsdTile, in.car + at, tile_n * 8, &bar[b]);
+#else
+    memcpy(s_key + b * kLsdTile, in.key + at, tile_n * 8);
+    memcpy(s_pos + b * kLsdTile, in.pos + at, tile_n * 4);
+    if (kCar) memcpy(s_car + b * kLsdTile, in.car + at, tile_n * 8);
+#endif
+  };
+
+  if (threadIdx.x == 0)
+  {
+#ifndef SZ4_EMU
+    for (uint32_t b = 0; b < 2; b++)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(lsd_smem_u32(&bar[b])), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#endif
+    s_next = atomicAdd(tile_counter, 1u);                             // tiles are handed out in starting order
+  }
+  __syncthreads();
+  uint32_t tile = s_next;
+  if (threadIdx.x == 0 && tile < total_tiles) fetch(tile, 0);
+  uint32_t phase0 = 0, phase1 = 0;
+  uint32_t b = 0;
+  while (tile < total_tiles)
+  {
+    __syncthreads();                                                   // everybody has read s_next; the other half is free
+    if (threadIdx.x == 0)
+    {
+      const uint32_t nx = kPersist ? atomicAdd(tile_counter, 1u) : 0xffffffffu;
+      s_next = nx;
+      if (nx < total_tiles) fetch(nx, b ^ 1);
+    }
+    for (uint32_t k = threadIdx.x; k < kLsd2Warps * kLsdBins; k += kLsd2Threads) (&cnt[0][0])[k] = 0;
+    const uint32_t chunk = tile / kLsdTilesPerChunk, ltile = tile % kLsdTilesPerChunk;
+    const uint32_t n = lg.count(chunk), tile_base = ltile * kLsdTile;
+    const bool empty = tile_base >= n;
+    const uint32_t tile_n = empty ? 0 : min((uint32_t)kLsdTile, n - tile_base);
+    const size_t region = (size_t)chunk * kLsdRegion;
+    // the element in front of the tile (for the table of the input order): asked for before the wait
+    uint64_t fk = 0; uint32_t fp = 0;
+    if (kCarOut && threadIdx.x == 0 && !empty && tile_base > 0) { fk = in.key[region + tile_base - 1]; fp = in.pos[region + tile_base - 1]; }
+    if (!empty && !kFirst)
+    {
+#ifndef SZ4_EMU
+      asm volatile(
+          "{\n"
+          ".reg .pred p;\n"
+          "LSD_WAIT_%=:\n"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+          "@p bra LSD_DONE_%=;\n"
+          "bra LSD_WAIT_%=;\n"
+          "LSD_DONE_%=:\n"
+          "}\n" ::"r"(lsd_smem_u32(&bar[b])), "r"(b ? phase1 : phase0) : "memory");
+      if (b) phase1 ^= 1; else phase0 ^= 1;
+#endif
+    }
+    __syncthreads();                                                   // counters zeroed (and, emulated, the tile copied)
+    const uint64_t* t_key = s_key + b * kLsdTile;
+    uint64_t* t_car = s_car + b * kLsdTile;
+    const uint32_t* t_pos = s_pos + b * kLsdTile;
+    if (!empty)
+    {
+      // ---- warp w owns elements [w*256, (w+1)*256) of the tile, as 8 rows of 32 in order
+      const uint32_t wbase = warp * (32 * kLsd2Items);
+      uint64_t key[kLsd2Items];
+      uint32_t rank[kLsd2Items];
+#pragma unroll
+      for (uint32_t r = 0; r < kLsd2Items; r++)
+      {
+        const uint32_t e = wbase + r * 32 + lane;
+        if (kFirst)
+        {
+          key[r] = e < tile_n ? lsd_key(data, (uint32_t)lg.lo(chunk) + tile_base + e) : 0;
+          (s_key + b * kLsdTile)[e] = key[r];
+        }
+        else key[r] = e < tile_n ? t_key[e] : 0;
+      }
+      // ---- table of the input order: the left neighbour is the previous position with the same `level`-byte prefix
+      if (kCarOut)
+      {
+        const uint32_t keep = 64 - 8 * level;
+#pragma unroll
+        for (uint32_t r = 0; r < kLsd2Items; r++)
+        {
+          const uint32_t e = wbase + r * 32 + lane;
+          if (e < tile_n)
+          {
+            uint64_t lk = fk; uint32_t lp = fp;
+            if (e > 0) { lk = t_key[e - 1]; lp = t_pos[e - 1]; }
+            const uint32_t d = t_pos[e] - lp;
+            // both positions (anchor - level) must be ones the reference inserts (>= first)
+            const bool hit = (e > 0 || tile_base > 0) && ((key[r] ^ lk) << keep) == 0 && d <= kWindow && lp >= first + level;
+            const uint64_t old = kCar ? t_car[e] : 0;
+            t_car[e] = old | ((uint64_t)(hit ? d : 0u) << (16 * (level - 4)));
+          }
+        }
+      }
+      // ---- rank inside the warp: __match_any_sync ranks equal digits inside a row, per-warp counters rank rows
+#pragma unroll
+      for (uint32_t r = 0; r < kLsd2Items; r++)
+      {
+        const uint32_t e = wbase + r * 32 + lane;
+        const bool valid = e < tile_n;
+        const uint32_t digit = valid ? (uint32_t)(key[r] >> shift) & 255u : 0xffffffffu;
+        const uint32_t peers = __match_any_sync(0xffffffffu, digit);
+        const uint32_t leader = (uint32_t)__ffs((int)peers) - 1;
+        const uint32_t before = (uint32_t)__popc(peers & ((1u << lane) - 1));
+        uint32_t start = 0;
+        if (valid && lane == leader)
+        {
+          start = cnt[warp][digit];
+          cnt[warp][digit] = start + (uint32_t)__popc(peers);
+        }
+        start = __shfl_sync(0xffffffffu, start, (int)leader);
+        rank[r] = start + before;
+        __syncwarp();
+      }
+      __syncthreads();
+      // ---- per digit (one thread each): rank of the warps, the tile's count, the look-back over the chunk's tiles in front
+      if (threadIdx.x < kLsdBins)
+      {
+        const uint32_t d = threadIdx.x;
+        uint32_t run = 0;
+#pragma unroll
+        for (uint32_t w = 0; w < kLsd2Warps; w++)
+        {
+          const uint32_t c = cnt[w][d];
+          cnt[w][d] = run;
+          run += c;
+        }
+        lstart[d] = run;                                              // for now: this digit's count in the tile
+        uint64_t* mine = tile_state + (size_t)tile * kLsdBins + d;
+        uint32_t excl = 0;
+        if (ltile == 0) lsd_post(mine, lsd_word(2, pass, run));
+        else
+        {
+          lsd_post(mine, lsd_word(1, pass, run));
+          const uint32_t first_tile = tile - ltile;
+          bool done = false;
+          for (uint32_t t = tile; !done && t > first_tile; )
+          {
+            // four tiles in front per trip (their words are independent reads)
+            uint64_t s[4];
+#pragma unroll
+            for (uint32_t u = 0; u < 4; u++) s[u] = t >= first_tile + u + 1 ? lsd_peek(tile_state + (size_t)(t - 1 - u) * kLsdBins + d) : 0;
+#pragma unroll
+            for (uint32_t u = 0; u < 4; u++)
+            {
+              if (done || t < first_tile + u + 1) continue;
+              const uint64_t* there = tile_state + (size_t)(t - 1 - u) * kLsdBins + d;
+              uint32_t spins = 0;
+              while ((uint32_t)((s[u] >> 56) & 63u) != pass || (s[u] >> 62) == 0)
+              {
+                if (++spins > kLsdSpin) { *err = 1; done = true; break; }   // a tile in front never published: do not hang the GPU
+                s[u] = lsd_peek(there);
+              }
+              excl += (uint32_t)s[u];
+              if ((s[u] >> 62) == 2) done = true;
+            }
+            t = t >= 4 ? t - 4 : 0;
+          }
+          lsd_post(mine, lsd_word(2, pass, excl + run));
+        }
+        gbase[d] = bases[(chunk * kLsdPasses + (pass - 1)) * kLsdBins + d] + excl;
+      }
+      __syncthreads();
+      if (warp == 0)
+      {
+        // exclusive scan of the 256 counts: eight per lane
+        uint32_t c[kLsdBins / 32], sum = 0;
+#pragma unroll
+        for (uint32_t k = 0; k < kLsdBins / 32; k++) { c[k] = lstart[lane * (kLsdBins / 32) + k]; sum += c[k]; }
+        const uint32_t incl = warp_incl_scan(sum, lane);
+        uint32_t run = incl - sum;
+#pragma unroll
+        for (uint32_t k = 0; k < kLsdBins / 32; k++) { lstart[lane * (kLsdBins / 32) + k] = run; run += c[k]; }
+      }
+      __syncthreads();
+      // ---- slot of every element; its inverse goes to shared memory
+#pragma unroll
+      for (uint32_t r = 0; r < kLsd2Items; r++)
+      {
+        const uint32_t e = wbase + r * 32 + lane;
+        if (e < tile_n)
+        {
+          const uint32_t digit = (uint32_t)(key[r] >> shift) & 255u;
+          s_src[lstart[digit] + cnt[warp][digit] + rank[r]] = (uint16_t)e;
+        }
+      }
+      __syncthreads();
+      // ---- out, in digit order: consecutive threads on consecutive addresses
+#pragma unroll
+      for (uint32_t m = 0; m < kLsd2Items; m++)
+      {
+        const uint32_t k = m * kLsd2Threads + threadIdx.x;
+        if (k < tile_n)
+        {
+          const uint32_t e = s_src[k];
+          const uint64_t kk = t_key[e];
+          const uint32_t digit = (uint32_t)(kk >> shift) & 255u;
+          const size_t dst = region + gbase[digit] + (k - lstart[digit]);
+          out.key[dst] = kk;
+          out.pos[dst] = kFirst ? (uint32_t)lg.lo(chunk) + tile_base + e : t_pos[e];
+          if (kCarOut) out.car[dst] = t_car[e];
+        }
+      }
+    }
+    tile = s_next;
+    if (kPersist) b ^= 1;
+  }
+}
+
 // The final order (all eight bytes): pe8 from the left neighbour, and the tables out by position:
 //   jump[a] = { pe4[a-4], pe5[a-5], pe6[a-6], pe7[a-7] }  (8 bytes per anchor),  pe8[a-8]  (its own array: the match
 //   finder stages a 64 KiB window of it in shared memory), and rank[a-8] = the element's index in the sorted arrays.

@@ -58,6 +58,9 @@ struct sz4_ctx
   int      debug_keep = 0;
   int      force_scalar = 0;
   int      allow_scalar_dict = 0;   // 1: a -D stream with a run > 60 000 bytes is replayed by one device thread (sz4_scalar.cuh)
+  int      lsd_persist = 0;    // 1 = passes 2..8 by persistent CTAs with two tiles in flight (slower: the look-back is exposed)
+  int      lsd_v1 = 0;         // 1 = passes 2..8 with the first form of the pass kernel (tests, comparisons)
+  uint32_t sm_count = 148;
   int      debug_stop = 0;     // tests: 1 = stop behind phase 1 (the tables stay for sz4_debug_fetch)
   uint32_t fast_hops = 64;     // k_search: at most this many candidates per lane and round in the fast loop ...
   uint32_t dense_a = 256, dense_b = 2048;   // k_search: first-two-hops distance below which a position goes in the first / second pass (0 = one pass)
@@ -86,7 +89,7 @@ struct sz4_ctx
   unsigned long long launches = 0;
   Geom               last_geom;
   bool               last_scalar = false;
-  bool               attr_set = false, dp_attr_set = false;
+  bool               attr_set = false, dp_attr_set = false, lsd_attr_set = false;
 
   int fail(const char* what, cudaError_t e)
   {
@@ -224,19 +227,43 @@ static int batch_submit(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
         CK(cudaMemsetAsync(ctx->lsd_state.p, 0, (size_t)tiles * kLsdBins * 8, ctx->stream));
         LAUNCH(ctx, k_lsd_hist, lg.chunks * kLsdHistSplit, 256, 0, (const uint8_t*)data, lg, common);
         LAUNCH(ctx, k_lsd_bases, lg.chunks, 256, 0, (const uint8_t*)data, lg, (const uint32_t*)common, bases);
+        if (!ctx->lsd_attr_set)
+        {
+          CK(cudaFuncSetAttribute(k_lsd_pass2<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lsd2Layout<2, false, true>::bytes));
+          CK(cudaFuncSetAttribute(k_lsd_pass2<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lsd2Layout<2, true, true>::bytes));
+          CK(cudaFuncSetAttribute(k_lsd_pass2<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lsd2Layout<2, true, true>::bytes));
+          CK(cudaFuncSetAttribute(k_lsd_pass2<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lsd2Layout<1, false, false>::bytes));
+          CK(cudaFuncSetAttribute(k_lsd_pass2<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lsd2Layout<1, false, true>::bytes));
+          CK(cudaFuncSetAttribute(k_lsd_pass2<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lsd2Layout<1, true, true>::bytes));
+          CK(cudaFuncSetAttribute(k_lsd_pass2<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lsd2Layout<1, true, true>::bytes));
+          ctx->lsd_attr_set = true;
+        }
         LsdBuf src = A, dst = A;
         for (uint32_t pass = 1; pass <= kLsdPasses; pass++)
         {
           const uint32_t level = pass >= 5 ? pass - 1 : 0;             // passes 5..8 read pe4..pe7 off their input order
-          if (pass == 1)
-            LAUNCH(ctx, (k_lsd_pass<true, false>), tiles, kLsdThreads, 0, src, dst, (const uint8_t*)data, lg, pass, level, first,
-                   (const uint32_t*)bases, (uint64_t*)ctx->lsd_state.p, counters + (pass - 1), counters + 8);
-          else if (pass <= 5)
-            LAUNCH(ctx, (k_lsd_pass<false, false>), tiles, kLsdThreads, 0, src, dst, (const uint8_t*)data, lg, pass, level, first,
-                   (const uint32_t*)bases, (uint64_t*)ctx->lsd_state.p, counters + (pass - 1), counters + 8);
-          else
-            LAUNCH(ctx, (k_lsd_pass<false, true>), tiles, kLsdThreads, 0, src, dst, (const uint8_t*)data, lg, pass, level, first,
-                   (const uint32_t*)bases, (uint64_t*)ctx->lsd_state.p, counters + (pass - 1), counters + 8);
+          const uint32_t mode = pass == 1 ? 0u : (pass <= 4 ? 1u : (pass == 5 ? 2u : 3u));
+          uint64_t* state = (uint64_t*)ctx->lsd_state.p;
+          uint32_t* cnt = counters + (pass - 1);
+          if (ctx->lsd_v1)
+          {
+            if (pass == 1) LAUNCH(ctx, (k_lsd_pass<true, false>), tiles, kLsdThreads, 0, src, dst, (const uint8_t*)data, lg, pass, level, first, (const uint32_t*)bases, state, cnt, counters + 8);
+            else if (pass <= 5) LAUNCH(ctx, (k_lsd_pass<false, false>), tiles, kLsdThreads, 0, src, dst, (const uint8_t*)data, lg, pass, level, first, (const uint32_t*)bases, state, cnt, counters + 8);
+            else LAUNCH(ctx, (k_lsd_pass<false, true>), tiles, kLsdThreads, 0, src, dst, (const uint8_t*)data, lg, pass, level, first, (const uint32_t*)bases, state, cnt, counters + 8);
+          }
+#define SZ4_PASS2(M, P, GRID, SMEM) LAUNCH(ctx, (k_lsd_pass2<M, P>), GRID, kLsd2Threads, SMEM, src, dst, (const uint8_t*)data, lg, pass, first, (const uint32_t*)bases, state, cnt, tiles, counters + 8)
+          else if (ctx->lsd_persist && pass > 1)
+          {
+            const uint32_t grid = tiles < ctx->sm_count ? tiles : ctx->sm_count;
+            if (mode == 1) SZ4_PASS2(1, true, grid, (Lsd2Layout<2, false, true>::bytes));
+            else if (mode == 2) SZ4_PASS2(2, true, grid, (Lsd2Layout<2, true, true>::bytes));
+            else SZ4_PASS2(3, true, grid, (Lsd2Layout<2, true, true>::bytes));
+          }
+          else if (mode == 0) SZ4_PASS2(0, false, tiles, (Lsd2Layout<1, false, false>::bytes));
+          else if (mode == 1) SZ4_PASS2(1, false, tiles, (Lsd2Layout<1, false, true>::bytes));
+          else if (mode == 2) SZ4_PASS2(2, false, tiles, (Lsd2Layout<1, true, true>::bytes));
+          else SZ4_PASS2(3, false, tiles, (Lsd2Layout<1, true, true>::bytes));
+#undef SZ4_PASS2
           src = dst;
           dst = (dst.key == A.key) ? B : A;
         }
@@ -840,6 +867,10 @@ int sz4_create(sz4_ctx** out, int device)
     delete ctx;
     return SZ4_ERR_CUDA;
   }
+  {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess && prop.multiProcessorCount > 0) ctx->sm_count = (uint32_t)prop.multiProcessorCount;
+  }
   const char* env = getenv("SZ4_STAGE_BULK");          // debugging aid: 0 = stage with plain loads
   if (env && env[0] == '0') ctx->stage_bulk = 0;
   *out = ctx;
@@ -888,6 +919,8 @@ int sz4_set_option(sz4_ctx* ctx, const char* name, long long value)
   if (!strcmp(name, "force_scalar")) { ctx->force_scalar = value != 0; return SZ4_OK; }
   if (!strcmp(name, "allow_scalar_dict")) { ctx->allow_scalar_dict = value != 0; return SZ4_OK; }
   if (!strcmp(name, "long_age")) { if (value < 0 || value > 1000000) return SZ4_ERR_ARG; ctx->long_age = (uint32_t)value; return SZ4_OK; }
+  if (!strcmp(name, "lsd_persist")) { ctx->lsd_persist = value != 0; return SZ4_OK; }
+  if (!strcmp(name, "lsd_v1")) { ctx->lsd_v1 = value != 0; return SZ4_OK; }
   if (!strcmp(name, "debug_stop")) { ctx->debug_stop = value != 0; return SZ4_OK; }
   ctx->err = "unknown option";
   return SZ4_ERR_ARG;

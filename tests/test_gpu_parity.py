@@ -287,7 +287,7 @@ def test_long_walk_kernel_agrees(gpu, age):
 
 def test_lz4_streams_with_bounded_memory():
     """smallz4::lz4 is a streaming call (smallz4.h:574-585, 770-780, 798-804): 1 GB comes out of a generator callback 64 KiB
-    at a time and the frame is hashed as it arrives, in a fresh process whose peak RSS stays under 1 GiB; the records
+    at a time and the frame is hashed as it arrives, in a fresh process whose peak RSS does not grow with the stream; the records
     are the reference's (first 64 blocks: golden digests; the rest: this library's committed 8 GB digests)."""
     import subprocess
     import sys
@@ -296,7 +296,10 @@ def test_lz4_streams_with_bounded_memory():
                        capture_output=True, text=True, check=True)
     out = json.loads(r.stdout.strip().splitlines()[-1])
     assert out["records"] == 256
-    assert out["peak_rss_kb"] < (1 << 20), f"peak RSS {out['peak_rss_kb']} KiB"
+    # bounded memory: 1 GB of input adds (next to) nothing to what a 192 MB stream needed -- CUDA context, device
+    # arrays and the four pinned halves (2 x 64 MiB in, 2 x 64 MiB out) -- and all of it stays far below the input size
+    grown = out["peak_rss_kb"] - out["rss_after_warmup_kb"]
+    assert grown < 32 * 1024, f"peak RSS grew by {grown} KiB with the stream's length"
     assert out["first_send_before_last_get"] and out["send_calls"] >= 16
     gold = _golden_blocks()["levels"]["9"]
     assert [d for d in out["sha256"][:64]] == [g["sha256"] for g in gold]
