@@ -363,16 +363,24 @@ k_lsd_pass(LsdBuf in, LsdBuf out, const uint8_t* data, LsdGeom lg, uint32_t pass
 // ---------------------------------------------------------------------------------------------
 enum : uint32_t
 {
-  kLsd2Threads = 512,
-  kLsd2Items   = kLsdTile / kLsd2Threads,                              // 8
+#ifndef SZ4_LSD2_THREADS
+#define SZ4_LSD2_THREADS 512
+#endif
+#ifndef SZ4_LSD2_CTAS
+#define SZ4_LSD2_CTAS 2
+#endif
+  kLsd2Threads = SZ4_LSD2_THREADS,
+  kLsd2Items   = 8,
+  kLsd2Tile    = kLsd2Threads * kLsd2Items,                            // elements per CTA
+  kLsd2TilesPerChunk = kLsdRegion / kLsd2Tile,
   kLsd2Warps   = kLsd2Threads / 32,
   kLsd2CntBytes = kLsd2Warps * kLsdBins * 4
 };
 // dynamic shared memory: kHalves input tiles (key, car, pos), slot -> element, per-warp digit counters, digit starts
 template <uint32_t kHalves, bool kWithCar, bool kWithPos> struct Lsd2Layout
 {
-  static constexpr uint32_t key = 0, car = key + kHalves * kLsdTile * 8, pos = car + (kWithCar ? kHalves * kLsdTile * 8 : 0),
-                            src = pos + (kWithPos ? kHalves * kLsdTile * 4 : 0), cnt = src + kLsdTile * 2, misc = cnt + kLsd2CntBytes,
+  static constexpr uint32_t key = 0, car = key + kHalves * kLsd2Tile * 8, pos = car + (kWithCar ? kHalves * kLsd2Tile * 8 : 0),
+                            src = pos + (kWithPos ? kHalves * kLsd2Tile * 4 : 0), cnt = src + kLsd2Tile * 2, misc = cnt + kLsd2CntBytes,
                             bytes = misc + 2 * kLsdBins * 4 + 64;
 };
 
@@ -394,7 +402,7 @@ __device__ __forceinline__ void lsd_bulk(void* dst, const void* src, uint32_t by
 // kPersist: one CTA per SM runs through the tiles, two halves of shared memory, the next tile's copies in flight while
 // this one is processed.  Otherwise: one tile per CTA, one half, two CTAs per SM (registers: 64 x 512 x 2).
 template <uint32_t kMode, bool kPersist>
-__global__ void __launch_bounds__(kLsd2Threads, kPersist ? 1 : 2)
+__global__ void __launch_bounds__(kLsd2Threads, kPersist ? 1 : SZ4_LSD2_CTAS)
 k_lsd_pass2(LsdBuf in, LsdBuf out, const uint8_t* data, LsdGeom lg, uint32_t pass, uint32_t first, const uint32_t* bases,
             uint64_t* tile_state, uint32_t* tile_counter, uint32_t total_tiles, uint32_t* err)
 {
@@ -418,23 +426,23 @@ k_lsd_pass2(LsdBuf in, LsdBuf out, const uint8_t* data, LsdGeom lg, uint32_t pas
   // input of tile `t` -> half `b`.  Sizes are rounded up to 16 bytes (the region has room: it is a multiple of the tile).
   auto fetch = [&](uint32_t t, uint32_t b)
   {
-    const uint32_t chunk = t / kLsdTilesPerChunk, ltile = t % kLsdTilesPerChunk;
-    const uint32_t n = lg.count(chunk), tile_base = ltile * kLsdTile;
+    const uint32_t chunk = t / kLsd2TilesPerChunk, ltile = t % kLsd2TilesPerChunk;
+    const uint32_t n = lg.count(chunk), tile_base = ltile * kLsd2Tile;
     if (tile_base >= n) return;                                        // an empty tile: nothing to wait for either
     if (kFirst) return;                                                // (pass 1 makes its elements itself)
-    const uint32_t tile_n = (min((uint32_t)kLsdTile, n - tile_base) + 3) & ~3u;
+    const uint32_t tile_n = (min((uint32_t)kLsd2Tile, n - tile_base) + 3) & ~3u;
     const size_t at = (size_t)chunk * kLsdRegion + tile_base;
 #ifndef SZ4_EMU
     const uint32_t bytes = tile_n * (kCar ? 20u : 12u);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the half was read and written by plain accesses before
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(lsd_smem_u32(&bar[b])), "r"(bytes) : "memory");
-    lsd_bulk(s_key + b * kLsdTile, in.key + at, tile_n * 8, &bar[b]);
-    lsd_bulk(s_pos + b * kLsdTile, in.pos + at, tile_n * 4, &bar[b]);
-    if (kCar) lsd_bulk(s_car + b * kLsdTile, in.car + at, tile_n * 8, &bar[b]);
+    lsd_bulk(s_key + b * kLsd2Tile, in.key + at, tile_n * 8, &bar[b]);
+    lsd_bulk(s_pos + b * kLsd2Tile, in.pos + at, tile_n * 4, &bar[b]);
+    if (kCar) lsd_bulk(s_car + b * kLsd2Tile, in.car + at, tile_n * 8, &bar[b]);
 #else
-    memcpy(s_key + b * kLsdTile, in.key + at, tile_n * 8);
-    memcpy(s_pos + b * kLsdTile, in.pos + at, tile_n * 4);
-    if (kCar) memcpy(s_car + b * kLsdTile, in.car + at, tile_n * 8);
+    memcpy(s_key + b * kLsd2Tile, in.key + at, tile_n * 8);
+    memcpy(s_pos + b * kLsd2Tile, in.pos + at, tile_n * 4);
+    if (kCar) memcpy(s_car + b * kLsd2Tile, in.car + at, tile_n * 8);
 #endif
   };
 
@@ -462,10 +470,10 @@ k_lsd_pass2(LsdBuf in, LsdBuf out, const uint8_t* data, LsdGeom lg, uint32_t pas
       if (nx < total_tiles) fetch(nx, b ^ 1);
     }
     for (uint32_t k = threadIdx.x; k < kLsd2Warps * kLsdBins; k += kLsd2Threads) (&cnt[0][0])[k] = 0;
-    const uint32_t chunk = tile / kLsdTilesPerChunk, ltile = tile % kLsdTilesPerChunk;
-    const uint32_t n = lg.count(chunk), tile_base = ltile * kLsdTile;
+    const uint32_t chunk = tile / kLsd2TilesPerChunk, ltile = tile % kLsd2TilesPerChunk;
+    const uint32_t n = lg.count(chunk), tile_base = ltile * kLsd2Tile;
     const bool empty = tile_base >= n;
-    const uint32_t tile_n = empty ? 0 : min((uint32_t)kLsdTile, n - tile_base);
+    const uint32_t tile_n = empty ? 0 : min((uint32_t)kLsd2Tile, n - tile_base);
     const size_t region = (size_t)chunk * kLsdRegion;
     // the element in front of the tile (for the table of the input order): asked for before the wait
     uint64_t fk = 0; uint32_t fp = 0;
@@ -486,9 +494,9 @@ k_lsd_pass2(LsdBuf in, LsdBuf out, const uint8_t* data, LsdGeom lg, uint32_t pas
 #endif
     }
     __syncthreads();                                                   // counters zeroed (and, emulated, the tile copied)
-    const uint64_t* t_key = s_key + b * kLsdTile;
-    uint64_t* t_car = s_car + b * kLsdTile;
-    const uint32_t* t_pos = s_pos + b * kLsdTile;
+    const uint64_t* t_key = s_key + b * kLsd2Tile;
+    uint64_t* t_car = s_car + b * kLsd2Tile;
+    const uint32_t* t_pos = s_pos + b * kLsd2Tile;
     if (!empty)
     {
       // ---- warp w owns elements [w*256, (w+1)*256) of the tile, as 8 rows of 32 in order
@@ -502,7 +510,7 @@ k_lsd_pass2(LsdBuf in, LsdBuf out, const uint8_t* data, LsdGeom lg, uint32_t pas
         if (kFirst)
         {
           key[r] = e < tile_n ? lsd_key(data, (uint32_t)lg.lo(chunk) + tile_base + e) : 0;
-          (s_key + b * kLsdTile)[e] = key[r];
+          (s_key + b * kLsd2Tile)[e] = key[r];
         }
         else key[r] = e < tile_n ? t_key[e] : 0;
       }
@@ -618,8 +626,12 @@ k_lsd_pass2(LsdBuf in, LsdBuf out, const uint8_t* data, LsdGeom lg, uint32_t pas
           s_src[lstart[digit] + cnt[warp][digit] + rank[r]] = (uint16_t)e;
         }
       }
+      if (threadIdx.x < kLsdBins) gbase[threadIdx.x] -= lstart[threadIdx.x];   // (unsigned wrap is fine: only the sum with k is used)
       __syncthreads();
       // ---- out, in digit order: consecutive threads on consecutive addresses
+      uint64_t* o_key = out.key + region;
+      uint32_t* o_pos = out.pos + region;
+      uint64_t* o_car = out.car + region;
 #pragma unroll
       for (uint32_t m = 0; m < kLsd2Items; m++)
       {
@@ -629,10 +641,10 @@ k_lsd_pass2(LsdBuf in, LsdBuf out, const uint8_t* data, LsdGeom lg, uint32_t pas
           const uint32_t e = s_src[k];
           const uint64_t kk = t_key[e];
           const uint32_t digit = (uint32_t)(kk >> shift) & 255u;
-          const size_t dst = region + gbase[digit] + (k - lstart[digit]);
-          out.key[dst] = kk;
-          out.pos[dst] = kFirst ? (uint32_t)lg.lo(chunk) + tile_base + e : t_pos[e];
-          if (kCarOut) out.car[dst] = t_car[e];
+          const uint32_t dst = gbase[digit] + k;                      // (gbase: where the digit starts in the output minus where it starts in the tile)
+          o_key[dst] = kk;
+          o_pos[dst] = kFirst ? (uint32_t)lg.lo(chunk) + tile_base + e : t_pos[e];
+          if (kCarOut) o_car[dst] = t_car[e];
         }
       }
     }

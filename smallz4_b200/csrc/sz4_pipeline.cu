@@ -64,6 +64,7 @@ struct sz4_ctx
   int      debug_stop = 0;     // tests: 1 = stop behind phase 1 (the tables stay for sz4_debug_fetch)
   uint32_t fast_hops = 64;     // k_search: at most this many candidates per lane and round in the fast loop ...
   uint32_t dense_a = 256, dense_b = 2048;   // k_search: first-two-hops distance below which a position goes in the first / second pass (0 = one pass)
+  uint32_t tail_lanes = 0;    // k_search: with the tile's queue empty, a warp with fewer walking lanes than this hands its walks to k_long (0: never; measured: no gain)
   uint32_t long_age = 8;       // k_search: rounds after which a walk is handed to k_long (tests lower it)
   uint32_t fast_lanes = 8;     // ... which goes on in steps of eight while at least this many lanes are still walking
   // device memory (grow-only)
@@ -211,9 +212,10 @@ static int batch_submit(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
     {
       if (jump_tables)
       {
-        const uint32_t tiles = lg.chunks * kLsdTilesPerChunk;
+        const uint32_t tiles1 = lg.chunks * kLsdTilesPerChunk, tiles2 = lg.chunks * kLsd2TilesPerChunk;   // first / second form of the pass kernel
+        const uint32_t tiles = ctx->lsd_v1 ? tiles1 : tiles2, tiles_max = tiles1 > tiles2 ? tiles1 : tiles2;
         const size_t misc_words = (size_t)lg.chunks * kLsdBins + (size_t)lg.chunks * kLsdPasses * kLsdBins + 64;
-        RSV(lsd_state, (size_t)tiles * kLsdBins * 8 + 64);
+        RSV(lsd_state, (size_t)tiles_max * kLsdBins * 8 + 64);
         RSV(lsd_misc, misc_words * 4);
         RSV(jump, ((size_t)N + 64) * 8);
         RSV(rank, ((size_t)N + 64) * 4);
@@ -224,7 +226,7 @@ static int batch_submit(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
         A.key = (uint64_t*)ctx->scratch.p; A.car = A.key + lsd_stride; A.pos = (uint32_t*)(A.car + lsd_stride);
         B.key = (uint64_t*)(A.pos + lsd_stride); B.car = B.key + lsd_stride; B.pos = (uint32_t*)(B.car + lsd_stride);
         CK(cudaMemsetAsync(ctx->lsd_misc.p, 0, misc_words * 4, ctx->stream));
-        CK(cudaMemsetAsync(ctx->lsd_state.p, 0, (size_t)tiles * kLsdBins * 8, ctx->stream));
+        CK(cudaMemsetAsync(ctx->lsd_state.p, 0, (size_t)tiles_max * kLsdBins * 8, ctx->stream));
         LAUNCH(ctx, k_lsd_hist, lg.chunks * kLsdHistSplit, 256, 0, (const uint8_t*)data, lg, common);
         LAUNCH(ctx, k_lsd_bases, lg.chunks, 256, 0, (const uint8_t*)data, lg, (const uint32_t*)common, bases);
         if (!ctx->lsd_attr_set)
@@ -315,20 +317,23 @@ static int batch_submit(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
         LAUNCH(ctx, k_twice_save, div_up(g.n_blocks, 64), 64, 0, pe, saved_pe, g);
       }
 
-      // ---- helpers for runs of one byte (sz4_runs.cuh): only the undisturbed ring (no dictionary) uses them in the
-      // search; a dictionary stream only asks for its longest run (see compress_blocks)
+      // ---- helpers for runs of one byte (sz4_runs.cuh): run_fwd and ones_back from the run structure of the data.
+      // The search uses them only with the undisturbed ring (no dictionary); a dictionary stream asks for its longest
+      // run among the bytes the reference inserts (see compress_blocks).
       RSV(run_fwd, ((size_t)N + 64) * 4);
       RSV(ones_back, ((size_t)N + 64) * 2);
       {
-        const uint32_t fchunks = div_up(N, kFlagChunk);
-        RSV(flag_last, (size_t)fchunks * 4 + 64);
-        RSV(flag_carry, (size_t)fchunks * 4 + 64);
-        uint32_t* fl = (uint32_t*)ctx->flag_last.p;
-        uint32_t* fc = (uint32_t*)ctx->flag_carry.p;
-        FlagFwdRuns fr; fr.data = data; fr.n = N;
-        LAUNCH(ctx, k_flag_reduce<FlagFwdRuns>, fchunks, kFlagThreads, 0, fr, fl);
-        LAUNCH(ctx, k_flag_carry, 1, 32, 0, (const uint32_t*)fl, fc, fchunks);
-        LAUNCH(ctx, (k_flag_apply<FlagFwdRuns, uint32_t, true>), fchunks, kFlagThreads, 0, fr, (const uint32_t*)fc, (uint32_t*)ctx->run_fwd.p, 0xffffffffu);
+        const uint32_t rchunks = div_up(N, kRunChunk);
+        RSV(flag_last, (size_t)rchunks * 8 + 64);
+        RSV(flag_carry, (size_t)rchunks * 8 + 64);
+        uint32_t* cf = (uint32_t*)ctx->flag_last.p;
+        uint32_t* cl = cf + rchunks;
+        uint32_t* pb = (uint32_t*)ctx->flag_carry.p;
+        uint32_t* nb = pb + rchunks;
+        LAUNCH(ctx, k_run_reduce, rchunks, kRunThreads, 0, (const uint8_t*)data, N, cf, cl);
+        LAUNCH(ctx, k_run_carry, 1, 256, 0, (const uint32_t*)cf, (const uint32_t*)cl, rchunks, N, pb, nb);
+        LAUNCH(ctx, k_run_apply, rchunks, kRunThreads, 0, (const uint8_t*)data, N, (const uint32_t*)pb, (const uint32_t*)nb,
+               (uint32_t*)ctx->run_fwd.p, (uint16_t*)ctx->ones_back.p);
       }
       if (g.shift != 0)
       {
@@ -338,16 +343,6 @@ static int batch_submit(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
         // smallz4.h:557-563, is never looked at)
         LAUNCH(ctx, k_max_u32, 148 * 4, 256, 0, (const uint32_t*)ctx->run_fwd.p + g.first_ins, N - g.first_ins, longest);
         CK(cudaMemcpyAsync(ctx->h_seg_total + 8, longest, 4, cudaMemcpyDeviceToHost, ctx->stream));
-      }
-      if (g.shift == 0)
-      {
-        const uint32_t fchunks = div_up(N, kFlagChunk);
-        uint32_t* fl = (uint32_t*)ctx->flag_last.p;
-        uint32_t* fc = (uint32_t*)ctx->flag_carry.p;
-        FlagOnesBack fo; fo.pe = pe; fo.n = N;
-        LAUNCH(ctx, k_flag_reduce<FlagOnesBack>, fchunks, kFlagThreads, 0, fo, fl);
-        LAUNCH(ctx, k_flag_carry, 1, 32, 0, (const uint32_t*)fl, fc, fchunks);
-        LAUNCH(ctx, (k_flag_apply<FlagOnesBack, uint16_t, false>), fchunks, kFlagThreads, 0, fo, (const uint32_t*)fc, (uint16_t*)ctx->ones_back.p, 65535u);
       }
       // ---- phase 2: longest match per position
       const uint32_t tiles_per_block = div_up(g.block_size, kTile);
@@ -390,7 +385,7 @@ static int batch_submit(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
       LAUNCH(ctx, k_search, n_tiles, kSearchThreads, kSearchSmem, (const uint8_t*)data, (const uint16_t*)pe,
              (const uint32_t*)saved_pe, (const uint32_t*)ctx->run_fwd.p, (const uint16_t*)ctx->ones_back.p, mlen, mdist,
              tiles_per_block, g, ctx->stage_bulk, ctx->fast_hops, ctx->fast_lanes, ctx->dense_a, ctx->dense_b, (const uint32_t*)tile_order,
-             (const uint32_t*)tile_count, (const uint32_t*)tile_queue, long_list, long_count, long_cap, ctx->long_age);
+             (const uint32_t*)tile_count, (const uint32_t*)tile_queue, long_list, long_count, long_cap, ctx->long_age, ctx->tail_lanes);
       if (jump_tables)
         LAUNCH(ctx, k_long, 148 * 8, 256, 0, (const uint8_t*)data, (const uint64_t*)lsd_sorted.key, (const uint32_t*)lsd_sorted.pos,
                (const uint32_t*)ctx->rank.p, (const LongWalk*)long_list, (const uint32_t*)long_count, long_cap,
@@ -918,6 +913,7 @@ int sz4_set_option(sz4_ctx* ctx, const char* name, long long value)
   if (!strcmp(name, "profile")) { ctx->profile = value != 0; return SZ4_OK; }
   if (!strcmp(name, "force_scalar")) { ctx->force_scalar = value != 0; return SZ4_OK; }
   if (!strcmp(name, "allow_scalar_dict")) { ctx->allow_scalar_dict = value != 0; return SZ4_OK; }
+  if (!strcmp(name, "tail_lanes")) { if (value < 0 || value > 33) return SZ4_ERR_ARG; ctx->tail_lanes = (uint32_t)value; return SZ4_OK; }
   if (!strcmp(name, "long_age")) { if (value < 0 || value > 1000000) return SZ4_ERR_ARG; ctx->long_age = (uint32_t)value; return SZ4_OK; }
   if (!strcmp(name, "lsd_persist")) { ctx->lsd_persist = value != 0; return SZ4_OK; }
   if (!strcmp(name, "lsd_v1")) { ctx->lsd_v1 = value != 0; return SZ4_OK; }

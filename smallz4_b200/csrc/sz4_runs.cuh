@@ -1,9 +1,8 @@
-// sz4_runs.cuh -- two per-position helpers for byte runs, both "distance to the nearest flagged
-// position" scans (three small kernels each: per-chunk reduce, chunk carry, per-chunk apply):
+// sz4_runs.cuh -- two per-position helpers for byte runs (three small kernels: per-chunk reduce, chunk carry,
+// per-chunk apply):
 //
-//   run_fwd[p]  = number of bytes equal to data[p] starting at p          (flag: data[x] != data[x+1])
-//   ones_back[p] = number of consecutive positions p, p-1, ... whose previousExact entry is 1
-//                  (flag: pe[q] != 1), saturated at 65535
+//   run_fwd[p]   = number of bytes equal to data[p] starting at p
+//   ones_back[p] = number of consecutive positions p, p-1, ... whose 8-byte chain entry (pe8) is 1, saturated at 65535
 //
 // The match finder uses them to step over whole runs of chain candidates that the reference
 // visits one by one and provably rejects (sz4_search.cuh, "stretch").
@@ -12,106 +11,130 @@
 
 namespace sz4
 {
-enum : uint32_t { kFlagThreads = 256, kFlagItems = 16, kFlagChunk = kFlagThreads * kFlagItems };
 #define SZ4_NOFLAG 0xffffffffu
 
-// Direction-agnostic index mapping: scan index k -> array position.
-struct FlagFwdRuns      // scanning right-to-left over data: k = 0 is the last position
-{
-  const uint8_t* data; uint32_t n;
-  __device__ __forceinline__ uint32_t pos(uint32_t k) const { return n - 1 - k; }
-  __device__ __forceinline__ bool flag(uint32_t k) const { uint32_t x = n - 1 - k; return k == 0 || data[x] != data[x + 1]; }
-};
-struct FlagOnesBack     // scanning left-to-right over pe
-{
-  const uint16_t* pe; uint32_t n;
-  __device__ __forceinline__ uint32_t pos(uint32_t k) const { return k; }
-  __device__ __forceinline__ bool flag(uint32_t k) const { return pe[k] != 1; }
-};
+// ---------------------------------------------------------------------------------------------
+// Both helpers from the run structure of the data alone, in three launches (no dictionary).  A position x is a
+// boundary if a run starts there (x == 0 or data[x] != data[x-1]).  With s = the last boundary <= p and e = the first
+// boundary > p (or n):   run_fwd[p] = e - p;   pe8[p] == 1 (sz4_lsd.cuh) iff the nine bytes from p-1 on are equal, i.e.
+// p > s and e - p >= 8, and then all of s+1 .. p have it too:   ones_back[p] = p - s  (saturated), else 0.
+// ---------------------------------------------------------------------------------------------
+enum : uint32_t { kRunThreads = 256, kRunChunk = 4096, kRunWords = kRunChunk / 32 };
 
-// last flagged scan index inside each chunk (or SZ4_NOFLAG)
-template <typename F>
-__global__ void __launch_bounds__(kFlagThreads) k_flag_reduce(F f, uint32_t* chunk_last)
+__device__ __forceinline__ bool run_boundary(const uint8_t* data, uint32_t x) { return x == 0 || data[x] != data[x - 1]; }
+
+// first and last boundary of every chunk (SZ4_NOFLAG: none)
+__global__ void __launch_bounds__(kRunThreads) k_run_reduce(const uint8_t* data, uint32_t n, uint32_t* chunk_first, uint32_t* chunk_last)
 {
-  __shared__ uint32_t best;
-  if (threadIdx.x == 0) best = 0;
+  __shared__ uint32_t lo, hi;
+  if (threadIdx.x == 0) { lo = SZ4_NOFLAG; hi = 0; }
   __syncthreads();
-  const uint32_t base = blockIdx.x * kFlagChunk + threadIdx.x * kFlagItems;
-  uint32_t mine = 0;                                   // stored as index + 1, 0 = none
-  for (uint32_t k = 0; k < kFlagItems; k++)
+  const uint32_t base = blockIdx.x * kRunChunk;
+  uint32_t mn = SZ4_NOFLAG, mx = 0;                                  // mx: position + 1, 0 = none
+  for (uint32_t k = 0; k < kRunChunk / kRunThreads; k++)
   {
-    uint32_t i = base + k;
-    if (i < f.n && f.flag(i)) mine = i + 1;
+    const uint32_t x = base + k * kRunThreads + threadIdx.x;
+    if (x < n && run_boundary(data, x)) { mn = min(mn, x); mx = x + 1; }
   }
-  if (mine) atomicMax(&best, mine);
+  if (mx) { atomicMin(&lo, mn); atomicMax(&hi, mx); }
   __syncthreads();
-  if (threadIdx.x == 0) chunk_last[blockIdx.x] = best ? best - 1 : SZ4_NOFLAG;
+  if (threadIdx.x == 0) { chunk_first[blockIdx.x] = lo; chunk_last[blockIdx.x] = hi ? hi - 1 : SZ4_NOFLAG; }
 }
 
-// one warp: chunk_carry[c] = last flagged index before chunk c (exclusive max-scan, 32 chunks per step)
-__global__ void __launch_bounds__(32) k_flag_carry(const uint32_t* chunk_last, uint32_t* chunk_carry, uint32_t chunks)
+// one CTA: prev_b[c] = last boundary in the chunks in front of c, next_b[c] = first boundary behind c (or n)
+__global__ void __launch_bounds__(256) k_run_carry(const uint32_t* chunk_first, const uint32_t* chunk_last, uint32_t chunks, uint32_t n,
+                                                   uint32_t* prev_b, uint32_t* next_b)
 {
-  if (blockIdx.x != 0) return;
-  const uint32_t lane = threadIdx.x;
-  uint32_t run = 0;                                    // index + 1 of the last flag so far, 0 = none
-  // four steps of 32 chunks per round, their loads issued together (the scan itself is a dependent chain)
-  for (uint32_t c0 = 0; c0 < chunks; c0 += 128)
+  __shared__ uint32_t ws[8];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // forward: running maximum of (last boundary + 1)
+  uint32_t run = 0;
+  for (uint32_t c0 = 0; c0 < chunks; c0 += 256)
   {
-    uint32_t vv[4];
+    const uint32_t c = c0 + threadIdx.x;
+    const uint32_t v = c < chunks ? chunk_last[c] : SZ4_NOFLAG;
+    uint32_t incl = v == SZ4_NOFLAG ? 0 : v + 1;
 #pragma unroll
-    for (uint32_t u = 0; u < 4; u++) { const uint32_t c = c0 + 32 * u + lane; vv[u] = c < chunks ? chunk_last[c] : SZ4_NOFLAG; }
+    for (uint32_t d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl = max(incl, t); }
+    if (lane == 31) ws[warp] = incl;
+    __syncthreads();
+    uint32_t before = run;
+    for (uint32_t w = 0; w < warp; w++) before = max(before, ws[w]);
+    const uint32_t up = __shfl_up_sync(0xffffffffu, incl, 1);
+    const uint32_t excl = max(before, lane == 0 ? 0u : up);
+    if (c < chunks) prev_b[c] = excl ? excl - 1 : 0;                 // (position 0 is a boundary: chunk 0 never asks)
+    for (uint32_t w = 0; w < 8; w++) run = max(run, ws[w]);
+    __syncthreads();
+  }
+  // backward: running minimum of the first boundary
+  uint32_t runmin = n;
+  for (uint32_t c0 = 0; c0 < chunks; c0 += 256)
+  {
+    const uint32_t k = c0 + threadIdx.x;                             // k-th chunk from the end
+    const uint32_t c = chunks - 1 - k;
+    const uint32_t v = k < chunks ? chunk_first[c] : SZ4_NOFLAG;
+    uint32_t incl = v == SZ4_NOFLAG ? n : v;
 #pragma unroll
-    for (uint32_t u = 0; u < 4; u++)
+    for (uint32_t d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl = min(incl, t); }
+    if (lane == 31) ws[warp] = incl;
+    __syncthreads();
+    uint32_t before = runmin;
+    for (uint32_t w = 0; w < warp; w++) before = min(before, ws[w]);
+    const uint32_t up = __shfl_up_sync(0xffffffffu, incl, 1);
+    const uint32_t excl = min(before, lane == 0 ? n : up);
+    if (k < chunks) next_b[c] = excl;
+    for (uint32_t w = 0; w < 8; w++) runmin = min(runmin, ws[w]);
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(kRunThreads) k_run_apply(const uint8_t* data, uint32_t n, const uint32_t* prev_b, const uint32_t* next_b,
+                                                           uint32_t* run_fwd, uint16_t* ones_back)
+{
+  __shared__ uint32_t words[kRunWords];                              // boundary bits of the chunk
+  __shared__ uint32_t prev_nz[kRunWords], next_nz[kRunWords];       // nearest non-empty word at or in front of / at or behind (index + 1, 0 = none)
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t base = blockIdx.x * kRunChunk;
+  for (uint32_t k = 0; k < kRunChunk / kRunThreads; k++)
+  {
+    const uint32_t x = base + k * kRunThreads + threadIdx.x;
+    const uint32_t m = __ballot_sync(0xffffffffu, x < n && run_boundary(data, x));
+    if (lane == 0) words[k * (kRunThreads / 32) + warp] = m;
+  }
+  __syncthreads();
+  if (threadIdx.x < kRunWords)
+  {
+    // 128 words: each thread looks for its nearest non-empty word (the boundaries are dense in anything but long runs)
+    uint32_t a = 0, b = 0;
+    for (int i = (int)threadIdx.x; i >= 0; i--) if (words[i]) { a = (uint32_t)i + 1; break; }
+    for (uint32_t i = threadIdx.x; i < kRunWords; i++) if (words[i]) { b = i + 1; break; }
+    prev_nz[threadIdx.x] = a; next_nz[threadIdx.x] = b;
+  }
+  __syncthreads();
+  const uint32_t carry_s = prev_b[blockIdx.x], carry_e = next_b[blockIdx.x];
+  for (uint32_t k = 0; k < kRunChunk / kRunThreads; k++)
+  {
+    const uint32_t j = k * kRunThreads + threadIdx.x, p = base + j;
+    if (p >= n) break;
+    const uint32_t w = j >> 5, bit = j & 31;
+    const uint32_t le = words[w] & (0xffffffffu >> (31 - bit));      // boundaries at or in front of p in its word
+    uint32_t s;
+    if (le) s = base + w * 32 + (31 - (uint32_t)__clz((int)le));
+    else
     {
-      const uint32_t c = c0 + 32 * u + lane;
-      const uint32_t v = vv[u];
-      uint32_t incl = v == SZ4_NOFLAG ? 0 : v + 1;     // flags only move right: a later one is larger
-#pragma unroll
-      for (uint32_t d = 1; d < 32; d <<= 1)
-      {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl = max(incl, t);
-      }
-      uint32_t before = __shfl_up_sync(0xffffffffu, incl, 1);
-      before = lane == 0 ? run : max(before, run);
-      if (c < chunks) chunk_carry[c] = before ? before - 1 : SZ4_NOFLAG;
-      run = max(run, __shfl_sync(0xffffffffu, incl, 31));
+      const uint32_t wp = w > 0 ? prev_nz[w - 1] : 0;
+      s = wp ? base + (wp - 1) * 32 + (31 - (uint32_t)__clz((int)words[wp - 1])) : carry_s;
     }
-  }
-}
-
-// out(pos(i)) = i - (last flagged index <= i)  [+1 for runs: counts the element itself], saturated
-template <typename F, typename Out, bool kCountSelf>
-__global__ void __launch_bounds__(kFlagThreads) k_flag_apply(F f, const uint32_t* chunk_carry, Out* out, uint32_t cap)
-{
-  __shared__ uint32_t tlast[kFlagThreads];
-  const uint32_t base = blockIdx.x * kFlagChunk + threadIdx.x * kFlagItems;
-  uint32_t mine = 0;
-  for (uint32_t k = 0; k < kFlagItems; k++)
-  {
-    uint32_t i = base + k;
-    if (i < f.n && f.flag(i)) mine = i + 1;
-  }
-  tlast[threadIdx.x] = mine;
-  __syncthreads();
-  // last flag in earlier threads of the chunk (simple backward search; flags are dense in practice)
-  uint32_t prev = 0;
-  for (int t = (int)threadIdx.x - 1; t >= 0; t--)
-    if (tlast[t]) { prev = tlast[t]; break; }
-  if (!prev)
-  {
-    uint32_t c = chunk_carry[blockIdx.x];
-    prev = c == SZ4_NOFLAG ? 0 : c + 1;
-  }
-  for (uint32_t k = 0; k < kFlagItems; k++)
-  {
-    uint32_t i = base + k;
-    if (i >= f.n) break;
-    if (f.flag(i)) prev = i + 1;
-    // prev - 1 = last flagged index <= i (prev == 0: none)
-    uint32_t d = prev ? i - (prev - 1) : i + 1;
-    if (kCountSelf) d += 1;
-    out[f.pos(i)] = (Out)(d > cap ? cap : d);
+    const uint32_t gt = bit == 31 ? 0u : words[w] & (0xffffffffu << (bit + 1));   // boundaries behind p in its word
+    uint32_t e;
+    if (gt) e = base + w * 32 + ((uint32_t)__ffs((int)gt) - 1);
+    else
+    {
+      const uint32_t wn = w + 1 < kRunWords ? next_nz[w + 1] : 0;
+      e = wn ? base + (wn - 1) * 32 + ((uint32_t)__ffs((int)words[wn - 1]) - 1) : carry_e;
+    }
+    run_fwd[p] = e - p;
+    ones_back[p] = (p > s && e - p >= 8) ? (uint16_t)min(p - s, 65535u) : (uint16_t)0;
   }
 }
 

@@ -252,7 +252,7 @@ enum : uint32_t { kIdle = 0, kWalk = 1, kCheck = 2, kStretch = 3, kFinish = 4, k
 #ifndef SZ4_FAST_BLOCK
 #define SZ4_FAST_BLOCK 8
 #endif
-enum : uint32_t { kFastHops = SZ4_FAST_BLOCK, kTailLanes = 12 };   // candidates per lane between two looks at how many lanes still walk
+enum : uint32_t { kFastHops = SZ4_FAST_BLOCK };   // candidates per lane between two looks at how many lanes still walk
 
 // The rejecting path of the walk (smallz4.h:192-233) for up to `hops` candidates per lane; see k_search.
 __device__ __forceinline__ void fast_hops_loop(const SearchView& v, uint32_t hops, uint32_t& state, uint32_t& total, uint32_t& hop,
@@ -479,7 +479,7 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
          const uint16_t* ones_back, uint32_t* mlen, uint16_t* mdist, uint32_t tiles_per_block, Geom g, int use_bulk,
          uint32_t fast_hops, uint32_t fast_lanes, uint32_t dense_a, uint32_t dense_b, const uint32_t* tile_order,
          const uint32_t* tile_count, const uint32_t* tile_queue, LongWalk* long_list, uint32_t* long_count, uint32_t long_cap,
-         uint32_t long_age)
+         uint32_t long_age, uint32_t tail_lanes)
 {
   SZ4_DYN_SMEM(smem);
   __shared__ uint64_t bar;
@@ -714,7 +714,7 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
       const bool movable = (state == kWalk || state == kSlowWalk) && run == 0;
       const bool drained = __any_sync(0xffffffffu, exhausted);
       const uint32_t walking = __ballot_sync(0xffffffffu, state != kIdle);
-      hand_over = movable && (++age > long_age || (drained && (uint32_t)__popc(walking) < kTailLanes));
+      hand_over = movable && (++age > long_age || (drained && (uint32_t)__popc(walking) < tail_lanes));
     }
     if (hand_over)
     {
@@ -750,28 +750,26 @@ k_long(const uint8_t* data, const uint64_t* skey, const uint32_t* spos, const ui
   const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
   const uint32_t n = min(*count, cap);
   GlobalView v; v.g_data = data;
-  for (uint32_t e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < n; e += nwarps)
+  // the next walk's head (its entry, its rank, its key: three dependent trips to L2) is fetched while this one is walked
+  uint32_t e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  LongWalk nw; nw.p = 0; nw.len = 0; nw.dist = 0; nw.total = 0; nw.budget = 0;
+  uint32_t nr = 0; uint64_t nkey = 0;
+  if (e < n) { nw = list[e]; nr = rank[nw.p]; nkey = skey[nr]; }
+  for (; e < n; e += nwarps)
   {
-    const LongWalk w = list[e];
+    const LongWalk w = nw;
+    const uint32_t r = nr;
+    const uint64_t key_p = nkey;
+    if (e + nwarps < n) { nw = list[e + nwarps]; nr = rank[nw.p]; nkey = skey[nr]; }
     const uint32_t p = w.p, a = p + 8;
     uint32_t len = w.len, dist = w.dist, budget = w.budget;
     const uint32_t stop = block_end(g, (p - g.halo) / g.block_size) - kEndLiterals;
     const uint32_t limit = chain_limit(g, data, p, v.word_at(p));
     uint32_t tail = v.word_at(p + len - 3);
-    const uint32_t r = rank[p];
-    const uint64_t key_p = skey[r];
     const uint32_t lo = r / region_elems * region_elems;             // the chunk's first element
-    // the candidates are at r-1, r-2, ...; skip the ones the walk has seen (up to w.total back)
-    uint32_t k = 0;
-    for (;;)
-    {
-      const bool in = r >= lo + 1 + k + lane;
-      const bool seen = in && skey[r - 1 - k - lane] == key_p && spos[r - 1 - k - lane] + w.total >= a;
-      const uint32_t m = __ballot_sync(0xffffffffu, seen);         // (true for the nearest members, then false)
-      if (m != 0xffffffffu) { k += (uint32_t)__ffs((int)~m) - 1; break; }
-      k += 32;
-    }
+    // The candidates are at r-1, r-2, ...; the ones the lanes' walk has seen (up to w.total back) are passed over.
     // kLongWide x 32 candidates per step: their loads are in flight together (a step is two dependent trips to L2)
+    uint32_t k = 0;
     for (bool done = false; !done; )
     {
       uint32_t a2[kLongWide]; bool valid[kLongWide], pass[kLongWide];
@@ -788,7 +786,7 @@ k_long(const uint8_t* data, const uint64_t* skey, const uint32_t* spos, const ui
       for (uint32_t u = 0; u < kLongWide; u++)
       {
         valid[u] = valid[u] && a - a2[u] <= limit;                   // a member of the chain (smallz4.h:192-197)
-        pass[u] = valid[u] && v.word_at(a2[u] - 8 + len - 3) == tail;
+        pass[u] = valid[u] && a - a2[u] > w.total && v.word_at(a2[u] - 8 + len - 3) == tail;
       }
       uint32_t advance = kLongWide * 32;
 #pragma unroll

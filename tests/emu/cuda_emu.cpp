@@ -120,11 +120,11 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& fn)
     c.fibers.assign(block.x, Fiber());
     c.warps.assign(block.x / 32, Warp());
     for (auto& w : c.warps) { w.slot[0].arrived = w.slot[1].arrived = 0; w.alive = 0xffffffffu; }
-    c.alive = block.x; c.bar_arrived = 0; c.bar_gen = 0; c.progress = 0;
+    c.alive = block.x; c.bar_arrived = 0; c.bar_gen = 0; c.progress = 0; c.or_val[0] = c.or_val[1] = 0;
     for (unsigned t = 0; t < block.x; t++)
     {
       Fiber& f = c.fibers[t];
-      f.tid = uint3_emu{ t, 0, 0 }; f.lane = t & 31; f.warp = t >> 5; f.coll_seq = 0; f.done = false;
+      f.tid = uint3_emu{ t, 0, 0 }; f.lane = t & 31; f.warp = t >> 5; f.coll_seq = 0; f.or_seq = 0; f.done = false;
       prepare(f);
     }
     while (c.alive)

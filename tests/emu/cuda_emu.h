@@ -53,6 +53,7 @@ struct Fiber
   uint3_emu tid{ 0, 0, 0 };
   int lane = 0, warp = 0;
   uint64_t coll_seq = 0;
+  unsigned or_seq = 0;
   bool done = false;
 };
 struct Cta
@@ -62,6 +63,7 @@ struct Cta
   unsigned alive = 0, bar_arrived = 0;
   uint64_t bar_gen = 0;
   uint64_t progress = 0;
+  int or_val[2] = { 0, 0 };
 };
 
 extern Fiber* cur;
@@ -97,6 +99,19 @@ static inline void __syncthreads()
     if (c->bar_arrived >= c->alive) { c->bar_arrived = 0; c->bar_gen++; c->progress++; return; }
     emu::yield();
   }
+}
+// barrier + OR of the predicate over the CTA (two slots in turn: a slot is cleared behind its second barrier, while
+// the next call already uses the other one)
+static inline int __syncthreads_or(int pred)
+{
+  emu::Cta* c = emu::cta;
+  const unsigned slot = emu::cur->or_seq++ & 1;
+  if (pred) c->or_val[slot] = 1;
+  __syncthreads();
+  const int r = c->or_val[slot];
+  __syncthreads();
+  c->or_val[slot] = 0;
+  return r;
 }
 static inline void emu_check_mask(unsigned mask)
 {

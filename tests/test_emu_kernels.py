@@ -95,13 +95,14 @@ def test_periodic_data_leaves_the_cost_ring(emu):
 @pytest.mark.parametrize("age", [0, 2])
 def test_long_walks_are_handed_to_k_long(age):
     """k_search hands walks that go on for many rounds to k_long (one warp per walk over the sorted arrays); with the
-    threshold at 0 or 2 rounds nearly every walk takes that path.  Several chunks of the sort, block borders included."""
-    c = emu_compressor(block_size=BS, batch_blocks=2, long_age=age)
+    threshold at 0 or 2 rounds nearly every walk takes that path.  Two chunks of the sort, a block border included."""
+    c = emu_compressor(block_size=BS, batch_blocks=2, long_age=age, tail_lanes=8 * age)
     try:
-        for kind, n, level in [("mixed", 3 * BS + 777, 9), ("binary", 200_000, 9), ("text", 150_000, 7), ("binary", 150_000, 4)]:
+        cases = [("mixed", BS + 20_000, 9), ("binary", 50_000, 4)] if age == 0 else [("binary", 70_000, 9), ("text", 40_000, 7)]
+        for kind, n, level in cases:
             check(c, corpus.make(kind, n, 13).tobytes(), level)
-        check(c, (b"abcdefg" * 40000)[:250_000], 9)
-        check(c, (b"abcdefgh12345678" * 20000)[:300_000], 8)
+        check(c, (b"abcdefg" * 20000)[:30_000], 9)
+        check(c, (b"abcdefgh12345678" * 8000)[:40_000], 8)
     finally:
         c.close()
 
