@@ -152,13 +152,23 @@ class ClockSampler(threading.Thread):
 
 
 # --------------------------------------------------------------------------- our arm (GPU)
-# Algorithmic bytes per input position of each phase (DESIGN.md "Kernels"): what the phase has to read and write
-# once if nothing were re-read.
-PHASE_BYTES = {"sort": 1 + 8 * (12 + 12) + 4 * 16 + 10, "chain": 2 + 2 + 1 + 4, "search": 1 + 2 + 8 + 4 + 2, "fixup": 6,
-               "dp": 4 + 2 + 4 + 16, "path": 6, "emit": 2}
-PHASE_KERNEL = {"sort": "k_lsd_pass x8 (+ k_lsd_hist, k_lsd_extract)", "chain": "k_flag_* (run helpers), k_tile_cost/order",
-                "search": "k_search", "fixup": "k_seed_detect/k_seed_fix", "dp": "k_dp_spec (+ plan, verify)", "path": "k_path_*",
-                "emit": "k_emit"}
+# Algorithmic bytes per input position of each phase (DESIGN.md "Kernels"): what the phase has to read and write once if
+# nothing were re-read.  sort: the data once for the histogram; pass 1 reads the data and writes key + position (12 B);
+# passes 2-4 move 12 B in and out, pass 5 12 in / 20 out (the carried tables start), passes 6-8 20 in and out.
+PHASE_BYTES = {"sort": 1 + (1 + 12) + 3 * 24 + (12 + 20) + 3 * 40,
+               "chain": (20 + 8 + 2 + 4) + (1 + 4 + 2) + 2 + (8 + 2 + 1 + 4 + 4 + 2 + 2),      # extract, run helpers, tile cost, k_start
+               "search": 1 + 2 + 2 + 6, "fixup": 6, "dp": 4 + 2 + 4 + 16, "path": 6, "emit": 2}
+PHASE_KERNEL = {"sort": "k_lsd_pass2 x8 (+ k_lsd_hist, k_lsd_bases)",
+                "chain": "k_lsd_extract, k_run_*, k_tile_cost/order, k_start",
+                "search": "k_search (+ k_long)", "fixup": "k_seed_detect/k_seed_fix", "dp": "k_dp_spec (+ plan, verify)",
+                "path": "k_path_*", "emit": "k_emit"}
+# what ncu says limits the phase's main kernel (profiles/r2_summary.md has the counters)
+PHASE_LIMIT = {"sort": "HBM copies with a permutation; barrier and shared-memory stalls between the phases of a tile keep them at about "
+                       "half of the copy bandwidth",
+               "chain": "L2 latency (gathers inside the 64 KiB window) and scatters that meet in L2",
+               "search": "issue slots and shared-memory wavefronts of the chain walk (k_search); L2 latency (k_long): not HBM",
+               "fixup": "latency", "dp": "issue slots / dependent-issue latency of the cost recurrence: not HBM", "path": "latency",
+               "emit": "HBM"}
 STEP_BYTES = sum(PHASE_BYTES.values())
 
 
@@ -358,13 +368,19 @@ def run_ours(args, rank, world, local_rank, sharded):
             "phase_ms_per_step": {k: v / args.steps for k, v in phases.items()},
             "ranks": ranks,
             "compression_ratio": total / max(packed, 1),
-            "roofline": {"bound": "hbm", "limited_by": counters.get("limited_by", "see profiles/"), "kernel": PHASE_KERNEL[top],
+            "roofline": {"bound": "hbm", "limited_by": PHASE_LIMIT[top], "kernel": PHASE_KERNEL[top],
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (int(counters["dram_bytes_per_input_byte"] * mine) if "dram_bytes_per_input_byte" in counters else None),
                          "traffic_source": counters.get("capture"),
                          "peak_source": peak_kind, "algorithmic_bytes_per_input_byte": PHASE_BYTES[top], "ms_per_launch": top_ms,
                          "issue_frac": counters.get("issue_frac"), "smem_wavefront_frac": counters.get("smem_wavefront_frac"),
                          "active_lanes": counters.get("active_lanes"), "dram_frac": counters.get("dram_frac"),
+                         "phases": {k: {"ms": phases[k] / args.steps, "algorithmic_bytes_per_input_byte": PHASE_BYTES[k],
+                                        "achieved": PHASE_BYTES[k] * mine / max(phases[k] / args.steps * 1e-3, 1e-9) / 1e9,
+                                        "frac": PHASE_BYTES[k] * mine / max(phases[k] / args.steps * 1e-3, 1e-9) / 1e9 / peak,
+                                        "kernels": PHASE_KERNEL[k], "limited_by": PHASE_LIMIT[k],
+                                        **{c: v for c, v in ncu_counters().get(k, {}).items() if c != "capture"}}
+                                    for k in phases},
                          "step": {"algorithmic_bytes_per_input_byte": STEP_BYTES,
                                   "achieved": STEP_BYTES * mine / (kernel_ms / args.steps * 1e-3) / 1e9,
                                   "frac": STEP_BYTES * mine / (kernel_ms / args.steps * 1e-3) / 1e9 / peak}},

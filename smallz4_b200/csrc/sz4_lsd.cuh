@@ -16,10 +16,10 @@
 // the order of passes 4..7 anyway and pick up pe4..pe7 on the way (carried along in `car`); k_lsd_extract reads the
 // final order for pe8 and writes the tables out by position.
 //
-// A pass is one kernel: global digit offsets come from a byte histogram of the input (the digits of pass j are the
-// input bytes shifted by j), the rank of a tile inside its digits from a decoupled look-back over the tiles in front
-// of it (each tile publishes its digit counts, then the running sums), and the tile is put in digit order in shared
-// memory before it is written, so that a warp's store covers a few long pieces.  HBM-bound: 24-40 B per element and pass.
+// A pass is one kernel (k_lsd_pass2): global digit offsets come from a byte histogram of the input (the digits of pass
+// j are the input bytes shifted by j), the rank of a tile inside its digits from a decoupled look-back over the tiles in
+// front of it (each tile publishes its digit counts, then the running sums), and the tile leaves in digit order, so that
+// a warp's store covers a few long pieces.  HBM-bound by nature: 24-40 B per element and pass.
 #pragma once
 #include "sz4_device.cuh"
 #include "sz4_sort.cuh"
@@ -28,9 +28,7 @@ namespace sz4
 {
 enum : uint32_t
 {
-  kLsdThreads = 256,
-  kLsdItems   = 16,
-  kLsdTile    = kLsdThreads * kLsdItems,   // 4096 elements per CTA
+  kLsdTile    = 4096,                      // elements per tile (the regions are multiples of it)
   kLsdBins    = 256,
   kLsdPasses  = 8,
 #ifndef SZ4_LSD_CHUNK
@@ -39,7 +37,6 @@ enum : uint32_t
   kLsdChunk   = SZ4_LSD_CHUNK,             // anchors a chunk owns (a multiple of the tile)
   kLsdHalo    = 65536,                     // anchors in front of them that it sorts along: their possible predecessors
   kLsdRegion  = kLsdChunk + kLsdHalo,      // elements per chunk in the buffers (a multiple of the tile)
-  kLsdTilesPerChunk = kLsdRegion / kLsdTile,
   kLsdSpin    = 1u << 24                   // polls of one look-back slot before the kernel gives up (never in practice)
 };
 
@@ -156,210 +153,11 @@ __device__ __forceinline__ void lsd_post(uint64_t* p, uint64_t v)
 #endif
 }
 
-// kFirst: pass 1, elements are made from the data.  kCar: the input has a `car` array (passes 6..8).
-// level: 0, or the prefix length whose table is read off the input order (passes 5..8: 4..7).
-// grid = chunks * kLsdTilesPerChunk; element e of chunk c lives at c * kLsdRegion + e.
-template <bool kFirst, bool kCar>
-__global__ void __launch_bounds__(kLsdThreads, 3)
-k_lsd_pass(LsdBuf in, LsdBuf out, const uint8_t* data, LsdGeom lg, uint32_t pass, uint32_t level, uint32_t first,
-           const uint32_t* bases, uint64_t* tile_state, uint32_t* tile_counter, uint32_t* err)
-{
-  __shared__ uint32_t cnt[kLsdThreads / 32][kLsdBins];
-  __shared__ uint32_t lstart[kLsdBins], gbase[kLsdBins];
-  __shared__ uint64_t stage[kLsdTile];
-  __shared__ uint8_t sdig[kLsdTile];
-  __shared__ uint32_t s_tile;
-
-  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);       // tiles are handed out in starting order: a tile only
-  for (uint32_t k = threadIdx.x; k < (kLsdThreads / 32) * kLsdBins; k += kLsdThreads) (&cnt[0][0])[k] = 0;   // waits for running ones
-  __syncthreads();
-  const uint32_t tile = s_tile;
-  const uint32_t chunk = tile / kLsdTilesPerChunk, ltile = tile % kLsdTilesPerChunk;
-  const uint32_t n = lg.count(chunk);                               // elements of this chunk
-  const uint32_t tile_base = ltile * kLsdTile;
-  if (tile_base >= n) return;                                       // (nobody looks back at an empty tile)
-  const uint32_t tile_n = min((uint32_t)kLsdTile, n - tile_base);
-  const uint32_t shift = (pass - 1) * 8;
-  const size_t region = (size_t)chunk * kLsdRegion;
-  const uint32_t a_lo = (uint32_t)lg.lo(chunk);
-
-  // ---- load: warp w owns elements [w*512, (w+1)*512) of the tile, as 16 rows of 32 in order
-  const uint32_t wbase = tile_base + warp * (32 * kLsdItems);
-  uint64_t key[kLsdItems];
-  uint32_t extra[kLsdItems];                                        // first the table entry read off the input order, then the rank
-#pragma unroll
-  for (uint32_t r = 0; r < kLsdItems; r++)
-  {
-    const uint32_t i = wbase + r * 32 + lane;
-    if (kFirst) key[r] = i < n ? lsd_key(data, a_lo + i) : 0;
-    else key[r] = i < n ? in.key[region + i] : 0;
-  }
-  // ---- table of the input order: the left neighbour is the previous position with the same `level`-byte prefix
-  uint32_t pe[kLsdItems / 2];                                       // two 16-bit entries per register
-#pragma unroll
-  for (uint32_t r = 0; r < kLsdItems / 2; r++) pe[r] = 0;
-  if (level != 0)
-  {
-    uint32_t pos[kLsdItems];
-#pragma unroll
-    for (uint32_t r = 0; r < kLsdItems; r++)
-    {
-      const uint32_t i = wbase + r * 32 + lane;
-      pos[r] = i < n ? in.pos[region + i] : 0;
-    }
-    uint64_t pk = 0; uint32_t pp = 0;                               // element in front of the warp's first one
-    if (wbase > 0 && wbase < n && lane == 0) { pk = in.key[region + wbase - 1]; pp = in.pos[region + wbase - 1]; }
-    const uint32_t keep = 64 - 8 * level;
-#pragma unroll
-    for (uint32_t r = 0; r < kLsdItems; r++)
-    {
-      uint64_t lk = __shfl_up_sync(0xffffffffu, key[r], 1);
-      uint32_t lp = __shfl_up_sync(0xffffffffu, pos[r], 1);
-      if (lane == 0) { lk = pk; lp = pp; }
-      const uint32_t i = wbase + r * 32 + lane;
-      const uint32_t d = pos[r] - lp;
-      // both positions (anchor - level) must be ones the reference inserts (>= first)
-      const bool hit = i < n && i > 0 && ((key[r] ^ lk) << keep) == 0 && d <= kWindow && lp >= first + level;
-      if (hit) pe[r >> 1] |= d << (16 * (r & 1));
-      pk = __shfl_sync(0xffffffffu, key[r], 31);
-      pp = __shfl_sync(0xffffffffu, pos[r], 31);
-    }
-  }
-  // ---- rank inside the warp: __match_any_sync ranks equal digits inside a row, per-warp counters rank rows
-#pragma unroll
-  for (uint32_t r = 0; r < kLsdItems; r++)
-  {
-    const uint32_t i = wbase + r * 32 + lane;
-    const bool valid = i < n;
-    const uint32_t digit = valid ? (uint32_t)(key[r] >> shift) & 255u : 0xffffffffu;
-    const uint32_t peers = __match_any_sync(0xffffffffu, digit);
-    const uint32_t leader = (uint32_t)__ffs((int)peers) - 1;
-    const uint32_t before = (uint32_t)__popc(peers & ((1u << lane) - 1));
-    uint32_t start = 0;
-    if (valid && lane == leader)
-    {
-      start = cnt[warp][digit];
-      cnt[warp][digit] = start + (uint32_t)__popc(peers);
-    }
-    start = __shfl_sync(0xffffffffu, start, (int)leader);
-    extra[r] = start + before;
-    __syncwarp();
-  }
-  __syncthreads();
-  // ---- per digit (one thread each): rank of the warps, the tile's count, and the look-back over the chunk's tiles in front
-  {
-    const uint32_t d = threadIdx.x;
-    uint32_t run = 0;
-#pragma unroll
-    for (uint32_t w = 0; w < kLsdThreads / 32; w++)
-    {
-      const uint32_t c = cnt[w][d];
-      cnt[w][d] = run;
-      run += c;
-    }
-    lstart[d] = run;                                                // for now: this digit's count in the tile
-    uint64_t* mine = tile_state + (size_t)tile * kLsdBins + d;
-    uint32_t excl = 0;
-    if (ltile == 0) lsd_post(mine, lsd_word(2, pass, run));
-    else
-    {
-      lsd_post(mine, lsd_word(1, pass, run));
-      for (uint32_t t = tile; t-- > tile - ltile; )
-      {
-        const uint64_t* there = tile_state + (size_t)t * kLsdBins + d;
-        uint64_t s = lsd_peek(there);
-        uint32_t spins = 0;
-        while ((uint32_t)((s >> 56) & 63u) != pass || (s >> 62) == 0)
-        {
-          if (++spins > kLsdSpin) { *err = 1; break; }              // a tile in front never published: do not hang the GPU
-          s = lsd_peek(there);
-        }
-        excl += (uint32_t)s;
-        if ((s >> 62) == 2 || spins > kLsdSpin) break;
-      }
-      lsd_post(mine, lsd_word(2, pass, excl + run));
-    }
-    gbase[d] = bases[(chunk * kLsdPasses + (pass - 1)) * kLsdBins + d] + excl;
-  }
-  __syncthreads();
-  if (warp == 0)
-  {
-    // exclusive scan of the 256 counts: eight per lane
-    uint32_t c[kLsdBins / 32], sum = 0;
-#pragma unroll
-    for (uint32_t k = 0; k < kLsdBins / 32; k++) { c[k] = lstart[lane * (kLsdBins / 32) + k]; sum += c[k]; }
-    const uint32_t incl = warp_incl_scan(sum, lane);
-    uint32_t run = incl - sum;
-#pragma unroll
-    for (uint32_t k = 0; k < kLsdBins / 32; k++) { lstart[lane * (kLsdBins / 32) + k] = run; run += c[k]; }
-  }
-  __syncthreads();
-  // ---- the tile in digit order in shared memory, then out with consecutive threads on consecutive addresses;
-  // one array after the other through the same staging buffer (extra[] becomes the slot in the tile)
-#pragma unroll
-  for (uint32_t r = 0; r < kLsdItems; r++)
-  {
-    const uint32_t i = wbase + r * 32 + lane;
-    if (i < n)
-    {
-      const uint32_t digit = (uint32_t)(key[r] >> shift) & 255u;
-      extra[r] += lstart[digit] + cnt[warp][digit];
-      stage[extra[r]] = key[r];
-      sdig[extra[r]] = (uint8_t)digit;
-    }
-  }
-  __syncthreads();
-  uint32_t dst[kLsdItems];
-#pragma unroll
-  for (uint32_t m = 0; m < kLsdItems; m++)
-  {
-    const uint32_t k = m * kLsdThreads + threadIdx.x;
-    dst[m] = 0xffffffffu;
-    if (k < tile_n)
-    {
-      const uint32_t digit = sdig[k];
-      dst[m] = gbase[digit] + (k - lstart[digit]);
-      out.key[region + dst[m]] = stage[k];
-    }
-  }
-  __syncthreads();
-  uint32_t* stage32 = (uint32_t*)stage;
-#pragma unroll
-  for (uint32_t r = 0; r < kLsdItems; r++)
-  {
-    const uint32_t i = wbase + r * 32 + lane;
-    if (i < n) stage32[extra[r]] = kFirst ? a_lo + i : in.pos[region + i];
-  }
-  __syncthreads();
-#pragma unroll
-  for (uint32_t m = 0; m < kLsdItems; m++) if (dst[m] != 0xffffffffu) out.pos[region + dst[m]] = stage32[m * kLsdThreads + threadIdx.x];
-  if (level != 0 || kCar)
-  {
-    __syncthreads();
-#pragma unroll
-    for (uint32_t r = 0; r < kLsdItems; r++)
-    {
-      const uint32_t i = wbase + r * 32 + lane;
-      if (i < n)
-      {
-        uint64_t v = kCar ? in.car[region + i] : 0;
-        if (level != 0) v |= (uint64_t)((pe[r >> 1] >> (16 * (r & 1))) & 0xffffu) << (16 * (level - 4));
-        stage[extra[r]] = v;
-      }
-    }
-    __syncthreads();
-#pragma unroll
-    for (uint32_t m = 0; m < kLsdItems; m++) if (dst[m] != 0xffffffffu) out.car[region + dst[m]] = stage[m * kLsdThreads + threadIdx.x];
-  }
-}
-
 // ---------------------------------------------------------------------------------------------
-// Passes 2..8, second form: persistent CTAs (one per SM) whose input tiles arrive by bulk-async copies
-// (cp.async.bulk -> UBLKCP, completion on an mbarrier) two tiles deep, so the loads of the next tile are in flight
-// while this one is ranked and written.  The tile is read where the copy put it: ranking gives every element its slot,
-// the inverse (slot -> element) is written to shared memory, and the output loop gathers from the staged input and
-// stores with consecutive threads on consecutive addresses.  The look-back reads four predecessors per trip.
+// One pass.  A tile of 4096 elements arrives in shared memory by bulk-async copies (cp.async.bulk -> UBLKCP, completion
+// on an mbarrier) and is read where the copy put it: ranking gives every element its slot, the inverse (slot ->
+// element) is written to shared memory, and the output loop gathers from the staged input and stores with consecutive
+// threads on consecutive addresses.  The look-back reads four predecessors per trip.
 // ---------------------------------------------------------------------------------------------
 enum : uint32_t
 {

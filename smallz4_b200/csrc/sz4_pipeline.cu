@@ -59,7 +59,6 @@ struct sz4_ctx
   int      force_scalar = 0;
   int      allow_scalar_dict = 0;   // 1: a -D stream with a run > 60 000 bytes is replayed by one device thread (sz4_scalar.cuh)
   int      lsd_persist = 0;    // 1 = passes 2..8 by persistent CTAs with two tiles in flight (slower: the look-back is exposed)
-  int      lsd_v1 = 0;         // 1 = passes 2..8 with the first form of the pass kernel (tests, comparisons)
   uint32_t sm_count = 148;
   int      debug_stop = 0;     // tests: 1 = stop behind phase 1 (the tables stay for sz4_debug_fetch)
   uint32_t fast_hops = 64;     // k_search: at most this many candidates per lane and round in the fast loop ...
@@ -212,10 +211,9 @@ static int batch_submit(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
     {
       if (jump_tables)
       {
-        const uint32_t tiles1 = lg.chunks * kLsdTilesPerChunk, tiles2 = lg.chunks * kLsd2TilesPerChunk;   // first / second form of the pass kernel
-        const uint32_t tiles = ctx->lsd_v1 ? tiles1 : tiles2, tiles_max = tiles1 > tiles2 ? tiles1 : tiles2;
+        const uint32_t tiles = lg.chunks * kLsd2TilesPerChunk;
         const size_t misc_words = (size_t)lg.chunks * kLsdBins + (size_t)lg.chunks * kLsdPasses * kLsdBins + 64;
-        RSV(lsd_state, (size_t)tiles_max * kLsdBins * 8 + 64);
+        RSV(lsd_state, (size_t)tiles * kLsdBins * 8 + 64);
         RSV(lsd_misc, misc_words * 4);
         RSV(jump, ((size_t)N + 64) * 8);
         RSV(rank, ((size_t)N + 64) * 4);
@@ -226,7 +224,7 @@ static int batch_submit(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
         A.key = (uint64_t*)ctx->scratch.p; A.car = A.key + lsd_stride; A.pos = (uint32_t*)(A.car + lsd_stride);
         B.key = (uint64_t*)(A.pos + lsd_stride); B.car = B.key + lsd_stride; B.pos = (uint32_t*)(B.car + lsd_stride);
         CK(cudaMemsetAsync(ctx->lsd_misc.p, 0, misc_words * 4, ctx->stream));
-        CK(cudaMemsetAsync(ctx->lsd_state.p, 0, (size_t)tiles_max * kLsdBins * 8, ctx->stream));
+        CK(cudaMemsetAsync(ctx->lsd_state.p, 0, (size_t)tiles * kLsdBins * 8, ctx->stream));
         LAUNCH(ctx, k_lsd_hist, lg.chunks * kLsdHistSplit, 256, 0, (const uint8_t*)data, lg, common);
         LAUNCH(ctx, k_lsd_bases, lg.chunks, 256, 0, (const uint8_t*)data, lg, (const uint32_t*)common, bases);
         if (!ctx->lsd_attr_set)
@@ -243,18 +241,11 @@ static int batch_submit(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
         LsdBuf src = A, dst = A;
         for (uint32_t pass = 1; pass <= kLsdPasses; pass++)
         {
-          const uint32_t level = pass >= 5 ? pass - 1 : 0;             // passes 5..8 read pe4..pe7 off their input order
           const uint32_t mode = pass == 1 ? 0u : (pass <= 4 ? 1u : (pass == 5 ? 2u : 3u));
           uint64_t* state = (uint64_t*)ctx->lsd_state.p;
           uint32_t* cnt = counters + (pass - 1);
-          if (ctx->lsd_v1)
-          {
-            if (pass == 1) LAUNCH(ctx, (k_lsd_pass<true, false>), tiles, kLsdThreads, 0, src, dst, (const uint8_t*)data, lg, pass, level, first, (const uint32_t*)bases, state, cnt, counters + 8);
-            else if (pass <= 5) LAUNCH(ctx, (k_lsd_pass<false, false>), tiles, kLsdThreads, 0, src, dst, (const uint8_t*)data, lg, pass, level, first, (const uint32_t*)bases, state, cnt, counters + 8);
-            else LAUNCH(ctx, (k_lsd_pass<false, true>), tiles, kLsdThreads, 0, src, dst, (const uint8_t*)data, lg, pass, level, first, (const uint32_t*)bases, state, cnt, counters + 8);
-          }
 #define SZ4_PASS2(M, P, GRID, SMEM) LAUNCH(ctx, (k_lsd_pass2<M, P>), GRID, kLsd2Threads, SMEM, src, dst, (const uint8_t*)data, lg, pass, first, (const uint32_t*)bases, state, cnt, tiles, counters + 8)
-          else if (ctx->lsd_persist && pass > 1)
+          if (ctx->lsd_persist && pass > 1)
           {
             const uint32_t grid = tiles < ctx->sm_count ? tiles : ctx->sm_count;
             if (mode == 1) SZ4_PASS2(1, true, grid, (Lsd2Layout<2, false, true>::bytes));
@@ -916,7 +907,6 @@ int sz4_set_option(sz4_ctx* ctx, const char* name, long long value)
   if (!strcmp(name, "tail_lanes")) { if (value < 0 || value > 33) return SZ4_ERR_ARG; ctx->tail_lanes = (uint32_t)value; return SZ4_OK; }
   if (!strcmp(name, "long_age")) { if (value < 0 || value > 1000000) return SZ4_ERR_ARG; ctx->long_age = (uint32_t)value; return SZ4_OK; }
   if (!strcmp(name, "lsd_persist")) { ctx->lsd_persist = value != 0; return SZ4_OK; }
-  if (!strcmp(name, "lsd_v1")) { ctx->lsd_v1 = value != 0; return SZ4_OK; }
   if (!strcmp(name, "debug_stop")) { ctx->debug_stop = value != 0; return SZ4_OK; }
   ctx->err = "unknown option";
   return SZ4_ERR_ARG;
