@@ -27,7 +27,10 @@ enum : uint32_t
   kTile          = SZ4_TILE, // positions per CTA
   kLook          = SZ4_LOOK, // bytes staged behind the tile for match extension
   kHist          = 65536,    // history staged in front of the tile
-  kSearchThreads = 1024,
+#ifndef SZ4_SEARCH_THREADS
+#define SZ4_SEARCH_THREADS 1024
+#endif
+  kSearchThreads = SZ4_SEARCH_THREADS,
   kDataBytes     = kHist + kTile + kLook + 16,
   kChainElems    = kHist + 32 + kTile,
   kSearchSmem    = kDataBytes + 2 * kChainElems

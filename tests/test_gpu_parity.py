@@ -325,3 +325,22 @@ def test_lz4_callback_ragged_reads_and_levels(gpu):
         finally:
             gpu.set_option("stream_blocks", 32)
         assert b"".join(out) == gpu.compress(data, level=level, use_legacy_format=legacy)
+
+
+def test_one_gib_in_one_batch(gpu):
+    """The largest batch the library forms (256 blocks = 1 GiB in one set of launches: 32-bit positions, 1.1 G sort
+    elements): same records as in batches of 64 blocks -- the reference's for the first 64 blocks, the committed digests
+    of this library's own 8 GB run for all 256."""
+    n = 1 << 30
+    data = corpus.make("mixed", n, 1)
+    gpu.set_option("batch_blocks", 256)
+    try:
+        frame = gpu.compress(data, level=9)
+    finally:
+        gpu.set_option("batch_blocks", 64)
+    records = _block_records(frame)
+    assert len(records) == 256
+    _check_blocks(records[:64], 9)
+    with open(os.path.join(os.path.dirname(__file__), "golden", "blocks_8gb_selfcheck.json")) as f:
+        self8 = json.load(f)["sha256_16"]
+    assert [digest(r)[:16] for r in records] == self8[:256]

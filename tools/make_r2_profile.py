@@ -21,7 +21,7 @@ SMS = 148
 INPUT_BYTES = 256 << 20
 PHASE_OF = {"k_lsd_pass2": "sort", "k_lsd_hist": "sort", "k_lsd_extract": "chain", "k_run_apply": "chain", "k_start": "chain",
             "k_search": "search", "k_long": "search", "k_dp_spec": "dp"}
-MAIN = {"sort": "k_lsd_pass2", "chain": "k_start", "search": "k_search", "dp": "k_dp_spec"}
+MAIN = {"sort": "k_lsd_pass2<3", "chain": "k_start", "search": "k_search", "dp": "k_dp_spec"}
 
 
 def num(x):
@@ -105,7 +105,7 @@ def main():
         # DRAM bytes of every captured launch that belongs to the phase, per input byte
         phase_bytes = sum((x["dram_read_gb"] + x["dram_write_gb"]) * 1e9 for k, v in per_kernel.items()
                           for x in v if PHASE_OF.get(k.split("<")[0], None) == phase)
-        counters[phase] = {"kernel": kern, "issue_frac": round(e["issue_frac"], 4), "smem_wavefront_frac": round(e["smem_wavefront_frac"], 4),
+        counters[phase] = {"kernel": match[0], "issue_frac": round(e["issue_frac"], 4), "smem_wavefront_frac": round(e["smem_wavefront_frac"], 4),
                            "active_lanes": round(e["active_lanes"], 2), "dram_frac": round(e["dram_frac"], 4),
                            "dram_bytes_per_input_byte": round(phase_bytes / INPUT_BYTES, 2),
                            "capture": f"profiles/{tag}.ncu-rep summary in profiles/r2_summary.md: ncu --set full --clock-control none of "
