@@ -110,7 +110,8 @@ long long sz4_last_dp_redos(const sz4_ctx* ctx);
 long long sz4_last_path_redos(const sz4_ctx* ctx);   /* same for the segments of the parse walk */
 
 /* test hook: copy an intermediate array of the last batch to the host (needs option debug_keep=1).
-   what: "pe" u16, "len_found" u32, "dist_found" u16, "len_final" u32, "cost" u32; count = elements */
+   what: "pe" u16 (previousExact as the reference's ring holds it), "pe8" u16, "jump" u64 (pe4..pe7 by anchor),
+   "len_found" u32, "dist_found" u16, "len_final" u32, "cost" u32; count = elements */
 int sz4_debug_fetch(sz4_ctx* ctx, const char* what, void* dst, size_t count);
 
 #ifdef __cplusplus

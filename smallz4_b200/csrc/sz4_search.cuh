@@ -1,16 +1,20 @@
 // sz4_search.cuh -- phase 2: longest match for every position (smallz4.h:173 findLongestMatch).
 //
-// One CTA per tile of kTile positions.  The CTA stages its slice of the input plus the 64 KiB of
-// history in front of it, and the previousExact entries of the same range, into shared memory
-// (cp.async.bulk -> SASS UBLKCP, completion on an mbarrier), then every lane walks the exact
-// chain of one position at a time.  Lanes that finish pull the next position of the tile
-// (persistent lanes) so that short and long chains mix inside a warp.
-//
-// The walk is a literal restatement of the reference loop, including what it does NOT check:
-// the first candidate is accepted without comparing bytes 0..1, later ones without byte 0
-// (harmless without a dictionary because chain members share their first four bytes; with a
-// dictionary the shifted ring makes it visible, DESIGN.md Q-dict).  Result: longest match,
-// nearest candidate on ties, at most max_chain improvements.
+// Without a dictionary (the normal case) the search is split three ways, all exact (DESIGN.md "The match finder"):
+//   k_start   one position per thread: the candidates the reference keeps while the match is shorter than 8 bytes are
+//             the nearest positions with the same 4, 5, .. 8 bytes -- read straight off the tables of sz4_lsd.cuh;
+//   k_search  one CTA per tile of kTile positions, for the searches that go on: the CTA stages its slice of the input
+//             plus the 64 KiB of history in front of it, and the 8-byte chain entries (pe8) of the same range, into
+//             shared memory (cp.async.bulk -> SASS UBLKCP, completion on an mbarrier); every lane walks the 8-byte
+//             chain of one position at a time and pulls the next one from the tile's queue when it is done
+//             (persistent lanes), so that short and long chains mix inside a warp;
+//   k_long    one warp per walk, for the few walks that go on for thousands of candidates: the chain is read 128
+//             members at a time from the sorted arrays.
+// With a dictionary k_search alone walks previousExact from the first candidate on, a literal restatement of the
+// reference loop including what it does NOT check: the first candidate is accepted without comparing bytes 0..1,
+// later ones without byte 0 (harmless without a dictionary because chain members share their first bytes; with a
+// dictionary the shifted ring makes it visible, DESIGN.md Q-dict).
+// Result either way: longest match, nearest candidate on ties, at most max_chain improvements.
 #pragma once
 #include "sz4_device.cuh"
 
@@ -119,10 +123,6 @@ struct SearchView
   uint32_t dlo, dhi, clo, shift;
 
   __device__ __forceinline__ uint32_t chain(uint32_t r) const { return lds_u16(s_pe + 2 * (r - shift - clo)); }
-  __device__ __forceinline__ uint32_t byte_at(uint32_t pos) const
-  {
-    return pos < dhi ? lds_u8(s_data + (pos - dlo)) : g_data[pos];
-  }
   __device__ __forceinline__ uint32_t word_at(uint32_t pos) const
   {
     if (pos + 4 <= dhi)

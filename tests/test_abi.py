@@ -29,7 +29,7 @@ def lib():
 
 def test_header_declares_the_expected_surface():
     names = declared_functions()
-    for must in ["sz4_create", "sz4_destroy", "sz4_lz4", "sz4_compress_host", "sz4_compress_device", "sz4_compress_bound",
+    for must in ["sz4_create", "sz4_destroy", "sz4_lz4", "sz4_compress_host", "sz4_compress_host_range", "sz4_compress_device", "sz4_compress_bound",
                  "sz4_version", "sz4_last_error", "sz4_frame_header", "sz4_frame_end", "sz4_set_option", "sz4_last_stats"]:
         assert must in names
 
