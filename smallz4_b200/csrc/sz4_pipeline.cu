@@ -1097,6 +1097,15 @@ int sz4_debug_tile_stats(unsigned* us, unsigned* t0, unsigned n)
 }
 #endif
 
+#ifdef SZ4_SEARCH_STATS
+int sz4_debug_search_stats(unsigned long long* out, int reset)
+{
+  if (cudaMemcpyFromSymbol(out, sz4::g_stats, 64) != cudaSuccess) return -1;
+  if (reset) { unsigned long long z[8] = { 0 }; cudaMemcpyToSymbol(sz4::g_stats, z, 64); }
+  return 0;
+}
+#endif
+
 const unsigned* sz4_debug_counters(const sz4_ctx* ctx) { return ctx ? (const unsigned*)(ctx->h_seg_total + 1) : nullptr; }
 long long sz4_last_path_redos(const sz4_ctx* ctx) { return ctx ? (long long)ctx->path_redos : -1; }
 

@@ -255,9 +255,15 @@ enum : uint32_t { kIdle = 0, kWalk = 1, kCheck = 2, kStretch = 3, kFinish = 4, k
 #ifndef SZ4_FAST_BLOCK
 #define SZ4_FAST_BLOCK 8
 #endif
-enum : uint32_t { kFastHops = SZ4_FAST_BLOCK };   // candidates per lane between two looks at how many lanes still walk
+#ifndef SZ4_STRETCHES
+#define SZ4_STRETCHES 8
+#endif
+enum : uint32_t { kFastHops = SZ4_FAST_BLOCK, kStretchesPerVisit = SZ4_STRETCHES };   // runs taken per visit of the slow part   // candidates per lane between two looks at how many lanes still walk
 
 // The rejecting path of the walk (smallz4.h:192-233) for up to `hops` candidates per lane; see k_search.
+#ifdef SZ4_SEARCH_STATS
+__device__ unsigned long long g_stats[8];   // 0 hop slots (lanes x hops offered), 1 useful hops, 2 rounds, 3 slow-part lane events, 4 refills, 5 slow-part warp passes
+#endif
 __device__ __forceinline__ void fast_hops_loop(const SearchView& v, uint32_t hops, uint32_t& state, uint32_t& total, uint32_t& hop,
                                                uint32_t run, uint32_t tail, smem_addr cbase, smem_addr dl, uint32_t min_lanes, uint32_t limit)
 {
@@ -296,6 +302,9 @@ __device__ __forceinline__ void fast_hops_loop(const SearchView& v, uint32_t hop
       uint32_t next_state = same ? kCheck : kWalk;                 // kCheck: worth a closer look
       if (ends) next_state = kFinish;
       if (go) total = tot2;
+#ifdef SZ4_SEARCH_STATS
+      { const uint32_t m = __ballot_sync(0xffffffffu, go); if ((threadIdx.x & 31) == 0) { atomicAdd(&g_stats[0], 32ull); atomicAdd(&g_stats[1], (unsigned long long)__popc(m)); } }
+#endif
       hop = hop2;
       if (walking) state = next_state;
     }
@@ -581,6 +590,7 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
           dl = v.s_data + (p + len - 3 - v.dlo);
           fast = p + len + 1 <= v.dhi || total + hop + v.dhi >= p + len + 1;
           state = fast ? kWalk : kSlowWalk;
+          if (run != 0 && hop == 1) state = kStretch;                  // inside a run: the closed form, right away
           age = 0;
         }
       }
@@ -646,6 +656,9 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
     // would need first differ.  A lane that meets anything else parks in a state for the slow part.
     // Written without branches around the loads: every lane executes the same 17 instructions per candidate.
     fast_hops_loop(v, fast_hops, state, total, hop, run, tail, cbase, dl, fast_lanes, limit);
+#ifdef SZ4_SEARCH_STATS
+    { const uint32_t m = __ballot_sync(0xffffffffu, state >= kCheck); if (lane == 0) { atomicAdd(&g_stats[2], 1ull); atomicAdd(&g_stats[3], (unsigned long long)__popc(m)); if (m) atomicAdd(&g_stats[5], 1ull); } }
+#endif
 
     // ---- slow part: candidates that passed the first byte, stretches, finished walks
     if (state >= kCheck)
@@ -678,6 +691,19 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
         else if (state == kStretch || (run != 0 && hop == 1))
         {
           finish = walk_stretch(v, run_fwd, ones_back, p, stop, run, total, hop, len, dist, budget, tail, limit);
+          // The chain goes on in the previous run of that byte (eight or more of it).  If it lands inside one -- the
+          // landing place's own entry is 1 again -- that run is the next stretch: taken right here instead of after
+          // another eight hops of the fast loop.  (A landing place with any other entry is a plain candidate.)
+#pragma unroll 1
+          for (uint32_t more = 0; more < kStretchesPerVisit && !finish; more++)
+          {
+            const uint32_t tot2 = total + hop;
+            if (hop == 0 || tot2 > limit) break;                       // the walk ends: the fast loop sees it
+            const uint32_t hop2 = lds_u16(cbase - 2 * tot2);
+            if (hop2 != 1) break;
+            total = tot2; hop = hop2;
+            finish = walk_stretch(v, run_fwd, ones_back, p, stop, run, total, hop, len, dist, budget, tail, limit);
+          }
         }
         else if (try_candidate(v, p, p - total, stop, len, tail, runs))
         {
