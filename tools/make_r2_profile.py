@@ -42,7 +42,7 @@ def main():
     a = ap.parse_args()
     tag = a.tag
     os.makedirs(P, exist_ok=True)
-    for f in (f"{tag}_bench.json", f"{tag}_bench_reference.json", f"{tag}_launches.csv", f"{tag}_bench_n2.json", f"{tag}_bench_reference_n2.json"):
+    for f in (f"{tag}_bench.json", f"{tag}_bench_reference.json", f"{tag}_launches.csv"):
         if os.path.exists(os.path.join(G, f)):
             shutil.copy(os.path.join(G, f), os.path.join(P, f))
     # ---- launch list
