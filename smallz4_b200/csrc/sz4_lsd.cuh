@@ -75,15 +75,15 @@ __device__ __forceinline__ uint64_t lsd_key(const uint8_t* data, uint32_t a)
 
 // ---- digit histograms per chunk: hist[c][v] = number of x in [lo(c) - 1, hi(c) - 8) with data[x] == v (the part all
 // passes have in common).  Indices are signed: the first anchors look at the zero padding in front of the batch.
-// grid = chunks * kLsdHistSplit.
+// grid = (number of chunks from chunk0 on) * kLsdHistSplit.
 enum : uint32_t { kLsdHistSplit = 8 };
 __global__ void __launch_bounds__(256)
-k_lsd_hist(const uint8_t* data, LsdGeom lg, uint32_t* hist)
+k_lsd_hist(const uint8_t* data, LsdGeom lg, uint32_t chunk0, uint32_t* hist)
 {
   __shared__ uint32_t h[kLsdBins];
   h[threadIdx.x] = 0;
   __syncthreads();
-  const uint32_t c = blockIdx.x / kLsdHistSplit, part = blockIdx.x % kLsdHistSplit;
+  const uint32_t c = chunk0 + blockIdx.x / kLsdHistSplit, part = blockIdx.x % kLsdHistSplit;
   const int32_t lo = lg.lo(c) - 1, hi = max(lg.hi(c) - 8, lo);
   // 16 aligned bytes per thread and step; equal neighbours are counted in a register first (runs of one byte would
   // otherwise serialise on one counter)
@@ -113,10 +113,10 @@ k_lsd_hist(const uint8_t* data, LsdGeom lg, uint32_t* hist)
 // one CTA of 256 threads per chunk: bases[c][j-1][v] = number of the chunk's anchors whose digit of pass j (data[a-j])
 // is below v.  Pass j looks at data[lo-j, hi-j) = the common part plus j-1 bytes in front and 8-j behind.
 __global__ void __launch_bounds__(256)
-k_lsd_bases(const uint8_t* data, LsdGeom lg, const uint32_t* common, uint32_t* bases)
+k_lsd_bases(const uint8_t* data, LsdGeom lg, uint32_t chunk0, const uint32_t* common, uint32_t* bases)
 {
   __shared__ uint32_t ws[32], tot;
-  const uint32_t c = blockIdx.x;
+  const uint32_t c = chunk0 + blockIdx.x;
   const int32_t a0 = lg.lo(c), a1 = lg.hi(c);
   const int32_t clo = a0 - 1, chi = max(a1 - 8, clo);
   for (int32_t j = 1; j <= (int32_t)kLsdPasses; j++)
@@ -202,7 +202,7 @@ __device__ __forceinline__ void lsd_bulk(void* dst, const void* src, uint32_t by
 template <uint32_t kMode, bool kPersist>
 __global__ void __launch_bounds__(kLsd2Threads, kPersist ? 1 : SZ4_LSD2_CTAS)
 k_lsd_pass2(LsdBuf in, LsdBuf out, const uint8_t* data, LsdGeom lg, uint32_t pass, uint32_t first, const uint32_t* bases,
-            uint64_t* tile_state, uint32_t* tile_counter, uint32_t total_tiles, uint32_t* err)
+            uint64_t* tile_state, uint32_t* tile_counter, uint32_t tile0, uint32_t total_tiles, uint32_t* err)
 {
   constexpr bool kFirst = kMode == 0, kCar = kMode == 3, kCarOut = kMode >= 2;
   const uint32_t level = kCarOut ? pass - 1 : 0;                     // the table read off the input order (passes 5..8: pe4..pe7)
@@ -251,7 +251,7 @@ k_lsd_pass2(LsdBuf in, LsdBuf out, const uint8_t* data, LsdGeom lg, uint32_t pas
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(lsd_smem_u32(&bar[b])), "r"(1));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 #endif
-    s_next = atomicAdd(tile_counter, 1u);                             // tiles are handed out in starting order
+    s_next = tile0 + atomicAdd(tile_counter, 1u);                     // tiles [tile0, total_tiles) are handed out in starting order
   }
   __syncthreads();
   uint32_t tile = s_next;
@@ -263,7 +263,7 @@ k_lsd_pass2(LsdBuf in, LsdBuf out, const uint8_t* data, LsdGeom lg, uint32_t pas
     __syncthreads();                                                   // everybody has read s_next; the other half is free
     if (threadIdx.x == 0)
     {
-      const uint32_t nx = kPersist ? atomicAdd(tile_counter, 1u) : 0xffffffffu;
+      const uint32_t nx = kPersist ? tile0 + atomicAdd(tile_counter, 1u) : 0xffffffffu;
       s_next = nx;
       if (nx < total_tiles) fetch(nx, b ^ 1);
     }

@@ -47,6 +47,11 @@ struct sz4_ctx
   cudaEvent_t  ev0 = nullptr, ev1 = nullptr;
   cudaStream_t copy_stream = nullptr;                 // input of the next batch / output of the previous one, next to the kernels
   cudaEvent_t  ev_in = nullptr, ev_out[2] = { nullptr, nullptr }, ev_user = nullptr;
+  // the input of a batch may arrive in up to eight pieces (compress_blocks): piece i ends at byte piece_end[i] of the batch
+  // buffer and ev_piece[i] fires when it is there; 0 pieces: the caller has made the stream wait for the whole input
+  enum { kMaxPieces = 8 };
+  cudaEvent_t  ev_piece[kMaxPieces] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+  uint32_t     piece_end[kMaxPieces] = { 0, 0, 0, 0, 0, 0, 0, 0 }, n_pieces = 0;
   cudaEvent_t  pev[8] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
   double       phase_ms[7] = { 0, 0, 0, 0, 0, 0, 0 };   // sort, chain, search, fixup, dp, path, emit
   int          profile = 0;
@@ -189,9 +194,19 @@ static int batch_submit(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
   CK(cudaMemsetAsync(mlen, 0, (size_t)N * 4, ctx->stream));
   CK(cudaMemsetAsync(mdist, 0, (size_t)N * 2, ctx->stream));
   PHASE(0);
+  // The input may still be on its way, piece by piece (the memsets above did not need it).  wait_pieces(k): the stream
+  // goes on when the first k pieces are there.
+  uint32_t pieces_waited = 0;
+  auto wait_pieces = [&](uint32_t upto) -> int
+  {
+    for (; pieces_waited < upto && pieces_waited < ctx->n_pieces; pieces_waited++)
+      CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_piece[pieces_waited], 0));
+    return SZ4_OK;
+  };
 
   if (scalar_finder)
   {
+    { int r = wait_pieces(ctx->n_pieces); if (r != SZ4_OK) return r; }
     // dictionary stream with runs long enough for the reference's long-run shortcut: the ring
     // semantics are replayed literally by one thread (sz4_scalar.cuh; DESIGN.md Q-dict)
     RSV(scalar_state, (sizeof(uint64_t) << kHashBits) + 2 * 65536 * sizeof(uint16_t));
@@ -219,14 +234,12 @@ static int batch_submit(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
         RSV(rank, ((size_t)N + 64) * 4);
         uint32_t* common = (uint32_t*)ctx->lsd_misc.p;
         uint32_t* bases = common + (size_t)lg.chunks * kLsdBins;
-        uint32_t* counters = bases + (size_t)lg.chunks * kLsdPasses * kLsdBins;   // [0..7] tile counters, [8] error flag
+        uint32_t* counters = bases + (size_t)lg.chunks * kLsdPasses * kLsdBins;   // [0..7] tile counters of the passes, [8] error flag, [9..16] pass 1 by piece
         LsdBuf A, B;
         A.key = (uint64_t*)ctx->scratch.p; A.car = A.key + lsd_stride; A.pos = (uint32_t*)(A.car + lsd_stride);
         B.key = (uint64_t*)(A.pos + lsd_stride); B.car = B.key + lsd_stride; B.pos = (uint32_t*)(B.car + lsd_stride);
         CK(cudaMemsetAsync(ctx->lsd_misc.p, 0, misc_words * 4, ctx->stream));
         CK(cudaMemsetAsync(ctx->lsd_state.p, 0, (size_t)tiles * kLsdBins * 8, ctx->stream));
-        LAUNCH(ctx, k_lsd_hist, lg.chunks * kLsdHistSplit, 256, 0, (const uint8_t*)data, lg, common);
-        LAUNCH(ctx, k_lsd_bases, lg.chunks, 256, 0, (const uint8_t*)data, lg, (const uint32_t*)common, bases);
         if (!ctx->lsd_attr_set)
         {
           CK(cudaFuncSetAttribute(k_lsd_pass2<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lsd2Layout<2, false, true>::bytes));
@@ -244,18 +257,37 @@ static int batch_submit(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
           const uint32_t mode = pass == 1 ? 0u : (pass <= 4 ? 1u : (pass == 5 ? 2u : 3u));
           uint64_t* state = (uint64_t*)ctx->lsd_state.p;
           uint32_t* cnt = counters + (pass - 1);
-#define SZ4_PASS2(M, P, GRID, SMEM) LAUNCH(ctx, (k_lsd_pass2<M, P>), GRID, kLsd2Threads, SMEM, src, dst, (const uint8_t*)data, lg, pass, first, (const uint32_t*)bases, state, cnt, tiles, counters + 8)
-          if (ctx->lsd_persist && pass > 1)
+#define SZ4_PASS2(M, P, GRID, SMEM, T0, T1) LAUNCH(ctx, (k_lsd_pass2<M, P>), GRID, kLsd2Threads, SMEM, src, dst, (const uint8_t*)data, lg, pass, first, (const uint32_t*)bases, state, cnt, T0, T1, counters + 8)
+          if (pass == 1)
+          {
+            // Histogram, digit offsets and pass 1 only look at the data: they run chunk range by chunk range behind the
+            // pieces of the input as they arrive, so that most of a host-to-device copy hides behind them.
+            const uint32_t np = ctx->n_pieces ? ctx->n_pieces : 1;
+            uint32_t c0 = 0;
+            for (uint32_t i = 0; i < np; i++)
+            {
+              { int r = wait_pieces(i + 1); if (r != SZ4_OK) return r; }
+              uint32_t c1 = lg.chunks;                                    // the last piece: everything that is left
+              if (i + 1 < np)
+                for (c1 = c0; c1 < lg.chunks && (uint32_t)lg.hi(c1) + 8 <= ctx->piece_end[i]; ) c1++;   // chunks whose bytes are all there
+              if (c1 == c0) continue;
+              LAUNCH(ctx, k_lsd_hist, (c1 - c0) * kLsdHistSplit, 256, 0, (const uint8_t*)data, lg, c0, common);
+              LAUNCH(ctx, k_lsd_bases, c1 - c0, 256, 0, (const uint8_t*)data, lg, c0, (const uint32_t*)common, bases);
+              cnt = counters + 9 + i;
+              SZ4_PASS2(0, false, (c1 - c0) * kLsd2TilesPerChunk, (Lsd2Layout<1, false, false>::bytes), c0 * kLsd2TilesPerChunk, c1 * kLsd2TilesPerChunk);
+              c0 = c1;
+            }
+          }
+          else if (ctx->lsd_persist)
           {
             const uint32_t grid = tiles < ctx->sm_count ? tiles : ctx->sm_count;
-            if (mode == 1) SZ4_PASS2(1, true, grid, (Lsd2Layout<2, false, true>::bytes));
-            else if (mode == 2) SZ4_PASS2(2, true, grid, (Lsd2Layout<2, true, true>::bytes));
-            else SZ4_PASS2(3, true, grid, (Lsd2Layout<2, true, true>::bytes));
+            if (mode == 1) SZ4_PASS2(1, true, grid, (Lsd2Layout<2, false, true>::bytes), 0u, tiles);
+            else if (mode == 2) SZ4_PASS2(2, true, grid, (Lsd2Layout<2, true, true>::bytes), 0u, tiles);
+            else SZ4_PASS2(3, true, grid, (Lsd2Layout<2, true, true>::bytes), 0u, tiles);
           }
-          else if (mode == 0) SZ4_PASS2(0, false, tiles, (Lsd2Layout<1, false, false>::bytes));
-          else if (mode == 1) SZ4_PASS2(1, false, tiles, (Lsd2Layout<1, false, true>::bytes));
-          else if (mode == 2) SZ4_PASS2(2, false, tiles, (Lsd2Layout<1, true, true>::bytes));
-          else SZ4_PASS2(3, false, tiles, (Lsd2Layout<1, true, true>::bytes));
+          else if (mode == 1) SZ4_PASS2(1, false, tiles, (Lsd2Layout<1, false, true>::bytes), 0u, tiles);
+          else if (mode == 2) SZ4_PASS2(2, false, tiles, (Lsd2Layout<1, true, true>::bytes), 0u, tiles);
+          else SZ4_PASS2(3, false, tiles, (Lsd2Layout<1, true, true>::bytes), 0u, tiles);
 #undef SZ4_PASS2
           src = dst;
           dst = (dst.key == A.key) ? B : A;
@@ -274,6 +306,7 @@ static int batch_submit(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
       }
       else
       {
+        { int r = wait_pieces(ctx->n_pieces); if (r != SZ4_OK) return r; }
         uint64_t* bufA = (uint64_t*)ctx->scratch.p;
         uint64_t* bufB = bufA + (((size_t)N + kPad + 1) & ~(size_t)1);
         const uint32_t tiles = div_up(count, kSortTile);
@@ -410,6 +443,7 @@ static int batch_submit(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
     else { PHASE(1); PHASE(2); PHASE(3); PHASE(4); }
   }
 
+  { int r = wait_pieces(ctx->n_pieces); if (r != SZ4_OK) return r; }        // (inputs too small for phase 1 come by here)
   if (ctx->debug_keep)
   {
     RSV(dbg_pe, (size_t)N * 2 + 64);
@@ -544,12 +578,6 @@ static int batch_finish(sz4_ctx* ctx)
   return SZ4_OK;
 }
 
-static int run_batch(sz4_ctx* ctx, const Geom& g, bool scalar_finder)
-{
-  int r = batch_submit(ctx, g, scalar_finder);
-  return r != SZ4_OK ? r : batch_finish(ctx);
-}
-
 // ---------------------------------------------------------------------------------------------
 // Stream driver: cuts [prefix | input] into batches of whole blocks with their halo
 // ---------------------------------------------------------------------------------------------
@@ -618,8 +646,8 @@ static int compress_blocks(sz4_ctx* ctx, const StreamJob& job, size_t* out_len)
   if (scalar && job.n + kWindow > max_batch_bytes) { ctx->err = "dictionary stream with long runs is limited to 1 GiB"; return SZ4_ERR_ARG; }
 
   // Batches are double-buffered: while the kernels of batch k run on ctx->stream, ctx->copy_stream brings in the
-  // input of batch k+1 and takes out the records of batch k-1.  run_batch always works on ctx->data / ctx->seg;
-  // the halves are swapped around it.  (run_batch returns after its kernels have finished: it reads the size.)
+  // input of batch k+1 and takes out the records of batch k-1.  batch_submit always works on ctx->data / ctx->seg;
+  // the halves are swapped around it.  The input itself comes in pieces, and the first kernels follow the pieces.
   auto geometry = [&](uint64_t kb, Geom& g, size_t& pay_lo, size_t& pay_hi, bool& batch_first)
   {
     const uint64_t ke = kb + per_batch < blocks_total ? kb + per_batch : blocks_total;
@@ -661,8 +689,27 @@ static int compress_blocks(sz4_ctx* ctx, const StreamJob& job, size_t* out_len)
       CK(cudaMemcpyAsync(d + kPad + kWindow, job.src + job.halo_in_src + pay_lo, pay_hi - pay_lo, in_kind, ctx->copy_stream));
     }
     else
-      CK(cudaMemcpyAsync(d + kPad, job.src + job.halo_in_src + pay_lo - g.halo, g.halo + (pay_hi - pay_lo), in_kind, ctx->copy_stream));
-    CK(cudaEventRecord(ctx->ev_in, ctx->copy_stream));
+    {
+      // in up to eight pieces that end on chunk borders of the sort: its first kernels follow the pieces (batch_submit)
+      const size_t all = g.halo + (pay_hi - pay_lo);
+      const uint8_t* from = job.src + job.halo_in_src + pay_lo - g.halo;
+      // (a device-to-device copy is over in no time: one piece)
+      const uint32_t np = (!job.src_on_device && all >= 16 * (size_t)kLsdChunk) ? 4u : 1u;
+      size_t at = 0;
+      for (uint32_t i = 0; i < np; i++)
+      {
+        const size_t end = i + 1 == np ? all : (all / np * (i + 1)) / kLsdChunk * kLsdChunk;
+        CK(cudaMemcpyAsync(d + kPad + at, from + at, end - at, in_kind, ctx->copy_stream));
+        CK(cudaEventRecord(ctx->ev_piece[i], ctx->copy_stream));
+        ctx->piece_end[i] = (uint32_t)end;
+        at = end;
+      }
+      ctx->n_pieces = np;
+      return SZ4_OK;
+    }
+    CK(cudaEventRecord(ctx->ev_piece[0], ctx->copy_stream));
+    ctx->piece_end[0] = g.n_total;
+    ctx->n_pieces = 1;
     return SZ4_OK;
   };
 
@@ -675,17 +722,18 @@ static int compress_blocks(sz4_ctx* ctx, const StreamJob& job, size_t* out_len)
     Geom g; size_t pay_lo, pay_hi; bool batch_first;
     geometry(kb, g, pay_lo, pay_hi, batch_first);
     std::swap(ctx->data, ctx->data2);                              // ctx->data: this batch's input, on its way
-    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_in, 0));
-    if (kb + per_batch < blocks_total)
-    {
-      // ctx->data2 held the previous batch's input, whose kernels have finished
-      int r = fetch(kb + per_batch);
-      if (r != SZ4_OK) { cudaStreamSynchronize(ctx->copy_stream); return r; }
-    }
     // ctx->seg is about to be written again: its last copy-out (two batches ago) must be over
     if (out_pending[slot]) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_out[slot], 0));
 
-    int r = run_batch(ctx, g, scalar);
+    int r = batch_submit(ctx, g, scalar);                          // (waits for the pieces of its input as it needs them)
+    if (r != SZ4_OK) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(ctx->stream); return r; }
+    if (kb + per_batch < blocks_total)
+    {
+      // ctx->data2 held the previous batch's input, whose kernels have finished
+      r = fetch(kb + per_batch);
+      if (r != SZ4_OK) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(ctx->stream); return r; }
+    }
+    r = batch_finish(ctx);
     if (r != SZ4_OK) { cudaStreamSynchronize(ctx->copy_stream); return r; }
     const size_t seg_len = (size_t)*ctx->h_seg_total;
     if (o + seg_len > job.cap) { cudaStreamSynchronize(ctx->copy_stream); ctx->err = "destination too small"; return SZ4_ERR_DST_SMALL; }
@@ -779,6 +827,7 @@ static int compress_stream(sz4_ctx* ctx, sz4_get_bytes get_bytes, sz4_send_bytes
     }
     std::swap(ctx->data, ctx->data2);
     CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_in, 0));
+    ctx->n_pieces = 0;
     int r = batch_submit(ctx, g, false);
     if (r != SZ4_OK) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(ctx->stream); return r; }
     // while the kernels run: push the previous records, pull the next batch
@@ -857,6 +906,8 @@ int sz4_create(sz4_ctx** out, int device)
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess && prop.multiProcessorCount > 0) ctx->sm_count = (uint32_t)prop.multiProcessorCount;
   }
+  for (int k = 0; k < sz4_ctx::kMaxPieces; k++)
+    if (cudaEventCreateWithFlags(&ctx->ev_piece[k], cudaEventDisableTiming) != cudaSuccess) { sz4_destroy(ctx); return SZ4_ERR_CUDA; }
   const char* env = getenv("SZ4_STAGE_BULK");          // debugging aid: 0 = stage with plain loads
   if (env && env[0] == '0') ctx->stage_bulk = 0;
   *out = ctx;
@@ -880,6 +931,7 @@ void sz4_destroy(sz4_ctx* ctx)
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   for (int k = 0; k < 8; k++) if (ctx->pev[k]) cudaEventDestroy(ctx->pev[k]);
   if (ctx->ev_in) cudaEventDestroy(ctx->ev_in);
+  for (int k = 0; k < sz4_ctx::kMaxPieces; k++) if (ctx->ev_piece[k]) cudaEventDestroy(ctx->ev_piece[k]);
   if (ctx->ev_user) cudaEventDestroy(ctx->ev_user);
   for (int k = 0; k < 2; k++) if (ctx->ev_out[k]) cudaEventDestroy(ctx->ev_out[k]);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);

@@ -127,3 +127,9 @@ def test_lz4_streams_batch_by_batch(n, level, legacy):
         assert len(out) >= 2 + (n > 2 * BS)            # header, records batch by batch, end mark: not one big push
     finally:
         c.close()
+
+
+def test_input_arriving_in_pieces(emu):
+    """From 16 sort chunks on (1 MiB in this build) the input of a batch is copied in four pieces and the histogram, the
+    digit offsets and pass 1 of the sort run piece by piece behind them: same frame."""
+    check(emu, corpus.make("mixed", 1_150_000, 19).tobytes(), 1)
