@@ -56,7 +56,8 @@ const char* sz4_version(void);
    timing for sz4_last_phase_ms), "force_scalar" (tests: route a dictionary stream through the scalar finder), "allow_scalar_dict" (a -D stream
    that contains 60 000 or more equal bytes in a row is refused with SZ4_ERR_ARG unless this is 1: then one device
    thread replays the reference's ring, exact but slow), "stream_blocks" (sz4_lz4: blocks per batch, bounds its pinned
-   host memory), "long_age" (match finder: rounds after which a walk moves to the warp-per-walk kernel);
+   host memory), "long_age" (match finder: rounds after which a walk moves to the warp-per-walk kernel), "tail_lanes" (0 = off:
+   hand a warp's last walks over when the tile's queue is empty), "lsd_persist" (sort passes by persistent CTAs);
    match-finder scheduling, results never depend on them: "fast_hops" (candidates per lane and round, 1..1024),
    "fast_lanes" (lanes that must still be walking for a round to go on, 0..32), "dense_a" / "dense_b" (positions
    whose first two chain hops add up to less than this go first / second; dense_a = 0: one pass) */
