@@ -378,7 +378,10 @@ k_tile_order(const uint32_t* cost, uint32_t n_tiles, uint32_t* order)
   }
 }
 
-enum : uint32_t { kLongWide = 4 };
+#ifndef SZ4_LONG_WIDE
+#define SZ4_LONG_WIDE 4
+#endif
+enum : uint32_t { kLongWide = SZ4_LONG_WIDE };
 struct LongWalk { uint32_t p, len, dist, total, budget; };     // a walk k_search hands to k_long: state behind its last candidate
 
 // How far back the reference's chain of position p reaches (no dictionary).  The tables of sz4_lsd.cuh are "pure"
