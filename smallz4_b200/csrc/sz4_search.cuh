@@ -817,7 +817,9 @@ k_long(const uint8_t* data, const uint64_t* skey, const uint32_t* spos, const ui
 #pragma unroll
       for (uint32_t u = 0; u < kLongWide; u++)
       {
-        valid[u] = valid[u] && a - a2[u] <= limit;                   // a member of the chain (smallz4.h:192-197)
+        // a member of the chain (smallz4.h:192-197); the sorted arrays start with a few anchors whose position lies in
+        // front of the batch (sz4_lsd.cuh leaves them out of the tables the same way): the chain ends there
+        valid[u] = valid[u] && a - a2[u] <= limit && a2[u] >= g.first_ins + 8;
         pass[u] = valid[u] && a - a2[u] > w.total && v.word_at(a2[u] - 8 + len - 3) == tail;
       }
       uint32_t advance = kLongWide * 32;

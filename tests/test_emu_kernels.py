@@ -133,3 +133,25 @@ def test_input_arriving_in_pieces(emu):
     """From 16 sort chunks on (1 MiB in this build) the input of a batch is copied in four pieces and the histogram, the
     digit offsets and pass 1 of the sort run piece by piece behind them: same frame."""
     check(emu, corpus.make("mixed", 1_150_000, 19).tobytes(), 1)
+
+
+def _class_reaching_in_front_of_the_batch(tail_bytes):
+    """150 times "seven zeros, the input's first byte, nine random bytes": the 8-byte class of those positions also holds
+    the anchor whose key is seven bytes of the zero padding in front of the batch plus the first byte -- a position at -7."""
+    r = corpus.make("random", 2000, 5).tobytes()
+    data = r[:20]
+    for i in range(150):
+        data += b"\0" * 7 + r[:1] + r[20 + 9 * i: 29 + 9 * i]
+    return data + corpus.make("text", tail_bytes, 5).tobytes()
+
+
+def test_k_long_stops_at_the_first_position_of_the_batch():
+    """The sorted arrays of the LSD sort begin with a few anchors whose position lies in front of the batch (their keys
+    contain the zero padding).  They sit at the far end of their class: the tables leave them out, and so must the walk
+    over the sorted arrays -- it used to read in front of the batch (found by tools/emu_asan_check.py)."""
+    c = emu_compressor(block_size=BS, batch_blocks=2, long_age=0)
+    try:
+        for level in (9, 2):
+            check(c, _class_reaching_in_front_of_the_batch(3000), level)
+    finally:
+        c.close()

@@ -344,3 +344,24 @@ def test_one_gib_in_one_batch(gpu):
     with open(os.path.join(os.path.dirname(__file__), "golden", "blocks_8gb_selfcheck.json")) as f:
         self8 = json.load(f)["sha256_16"]
     assert [digest(r)[:16] for r in records] == self8[:256]
+
+
+def _class_reaching_in_front_of_the_batch(tail_bytes):
+    """150 times "seven zeros, the input's first byte, nine random bytes": the 8-byte class of those positions also holds
+    the anchor whose key is seven bytes of the zero padding in front of the batch plus the first byte -- a position at -7."""
+    r = corpus.make("random", 2000, 5).tobytes()
+    data = r[:20]
+    for i in range(150):
+        data += b"\0" * 7 + r[:1] + r[20 + 9 * i: 29 + 9 * i]
+    return data + corpus.make("text", tail_bytes, 5).tobytes()
+
+
+def test_k_long_stops_at_the_first_position_of_the_batch(gpu):
+    """See the test of the same name in tests/test_emu_kernels.py: a class whose far end lies in front of the batch."""
+    data = _class_reaching_in_front_of_the_batch(300_000)
+    gpu.set_option("long_age", 0)
+    try:
+        for level in (9, 2):
+            assert gpu.compress(data, level=level) == oracle_compress(data, level)[0]
+    finally:
+        gpu.set_option("long_age", 8)
