@@ -774,7 +774,7 @@ k_search(const uint8_t* data, const uint16_t* pe, const uint32_t* saved_pe, cons
 // smallz4.h:224-225) runs on all 32 at once and only a candidate that passes it gets the closer look.  Same candidates
 // in the same order as the walk: same result.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 k_long(const uint8_t* data, const uint64_t* skey, const uint32_t* spos, const uint32_t* rank, const LongWalk* list,
        const uint32_t* count, uint32_t cap, const uint32_t* run_fwd, uint32_t* mlen, uint16_t* mdist, uint32_t region_elems, Geom g)
 {
@@ -782,6 +782,7 @@ k_long(const uint8_t* data, const uint64_t* skey, const uint32_t* spos, const ui
   const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
   const uint32_t n = min(*count, cap);
   GlobalView v; v.g_data = data;
+  const uint32_t a_min = g.first_ins + 8;                            // the first anchor whose position is in the batch
   // the next walk's head (its entry, its rank, its key: three dependent trips to L2) is fetched while this one is walked
   uint32_t e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   LongWalk nw; nw.p = 0; nw.len = 0; nw.dist = 0; nw.total = 0; nw.budget = 0;
@@ -812,14 +813,14 @@ k_long(const uint8_t* data, const uint64_t* skey, const uint32_t* spos, const ui
         const bool in = r >= lo + 1 + off;
         const uint32_t idx = in ? r - 1 - off : r;
         a2[u] = spos[idx];
-        valid[u] = in && skey[idx] == key_p;
+        // (the sorted arrays start with a few anchors whose position lies in front of the batch -- sz4_lsd.cuh leaves them
+        // out of the tables the same way: the chain ends there)
+        valid[u] = in && skey[idx] == key_p && a2[u] >= a_min;
       }
 #pragma unroll
       for (uint32_t u = 0; u < kLongWide; u++)
       {
-        // a member of the chain (smallz4.h:192-197); the sorted arrays start with a few anchors whose position lies in
-        // front of the batch (sz4_lsd.cuh leaves them out of the tables the same way): the chain ends there
-        valid[u] = valid[u] && a - a2[u] <= limit && a2[u] >= g.first_ins + 8;
+        valid[u] = valid[u] && a - a2[u] <= limit;                   // a member of the chain (smallz4.h:192-197)
         pass[u] = valid[u] && a - a2[u] > w.total && v.word_at(a2[u] - 8 + len - 3) == tail;
       }
       uint32_t advance = kLongWide * 32;
