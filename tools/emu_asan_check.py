@@ -40,6 +40,13 @@ def main():
             same = c.compress(data, level=level, use_legacy_format=legacy) == oracle_compress(data, level, legacy, block_size=bs)[0]
             print(age, kind, n, level, legacy, "equal" if same else "DIFF", flush=True)
             ok &= same
+        if age == 8:
+            d = corpus.make("text", 3000, 21, offset=1 << 40).tobytes()                # the dictionary path (round-1 kernels)
+            data = corpus.make("text", 50_000, 21).tobytes()
+            for level in (2, 9):
+                same = c.compress(data, level=level, dictionary=d) == oracle_compress(data, level, False, d, block_size=bs)[0]
+                print(age, "dictionary", level, "equal" if same else "DIFF", flush=True)
+                ok &= same
         data = corpus.make("mixed", 5 * bs + 99, 33).tobytes()
         pos, out = [0], []
 
