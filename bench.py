@@ -374,7 +374,7 @@ def run_ours(args, rank, world, local_rank, sharded):
             "config": {"workload": workload_name(total_mb), "level": 9, "block_bytes": BLOCK,
                        "sharding": (f"{world} contiguous ranges of whole blocks, one per GPU, each with a 128 KiB halo in front; no collective "
                                     f"on the data path" if world > 1 else "one GPU, whole stream"),
-                       "l2": f"every batch ({min(args.batch_blocks * 4, total_mb)} MB of input, ~50 B of arrays per byte) is larger than "
+                       "l2": f"every batch ({min(args.batch_blocks * 4, total_mb)} MB of input, ~75 B of arrays per byte) is larger than "
                              f"L2 (126 MB); no flush needed",
                        "batch_blocks": args.batch_blocks},
             "e2e": {"value": total * args.steps / dt_e2e / 1e9, "unit": "GB/s", "h2d_bytes_per_step": total + (world - 1) * HALO,
